@@ -1,0 +1,33 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return load_golden
+
+
+def rel_err(y, ref, floor=1e-6):
+    """max over rows of ||y - ref||_inf / max(||ref||_inf, floor) - the 1e-4 parity metric."""
+    y = np.asarray(y, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    num = np.abs(y - ref).reshape(len(ref), -1).max(axis=1)
+    den = np.maximum(np.abs(ref).reshape(len(ref), -1).max(axis=1), floor)
+    return float((num / den).max()) if len(ref) else 0.0
