@@ -1,0 +1,192 @@
+"""MeanAggregator / GCNAggregator / MaxPoolingAggregator - the surface of reference
+graphsage/aggregators.py:6-195 over the B200 kernels.
+
+Two entry points per aggregator:
+  agg((self_vecs[n, in], neigh_vecs[n, k, neigh_in])) -> [n, out * (2 if concat else 1)]
+      the reference call convention (dense, already-gathered inputs);
+  agg.aggregate_rows(src, segments) -> [rows, out_w]
+      the gather-fused form used by SampleAndAggregate.aggregate: neighbours are addressed by
+      id lists (or row ranges) into `src`, the [n*k, F] neighbour tensor is never materialised.
+"""
+import torch
+
+from . import ops
+from .inits import glorot, zeros
+from .layers import Dense, Layer, act_code, identity, relu  # noqa: F401  (relu/identity re-exported as `act` values)
+
+_DEFAULT_MATH = [ops.MATH_FP32_SIMT]
+_MATH_NAMES = {"fp32": ops.MATH_FP32_SIMT, "simt": ops.MATH_FP32_SIMT, "tf32x3": ops.MATH_TF32X3,
+               "tf32": ops.MATH_TF32, "bf16": ops.MATH_BF16}
+
+
+def set_default_math(mode):
+    """Arithmetic of the dense contraction for aggregators created afterwards: 'fp32' (CUDA cores),
+    'tf32x3' (tcgen05, fp32-accurate), 'tf32', 'bf16'."""
+    _DEFAULT_MATH[0] = _MATH_NAMES[mode] if isinstance(mode, str) else int(mode)
+
+
+def _dropout(x, p):
+    return torch.nn.functional.dropout(x, p=float(p), training=True) if p else x
+
+
+def _dense_segment(n, k):
+    return [ops.make_segment(n, k)]
+
+
+class _SageAggregator(Layer):
+    def _finish(self, parts, combine):
+        code, post = act_code(self.act)
+        y = ops.sage_gemm(parts, combine=combine, bias=self.vars.get("bias"), act=code, math=self.math)
+        return post(y) if post else y
+
+    @property
+    def output_width(self):
+        return self.output_dim * (2 if (self.concat and "self_weights" in self.vars) else 1)
+
+
+class MeanAggregator(_SageAggregator):
+    """act(concat_or_add(self @ self_weights, mean_k(neigh) @ neigh_weights)) - aggregators.py:43-64."""
+
+    def __init__(self, input_dim, output_dim, neigh_input_dim=None, dropout=0., bias=False, act=relu, name=None,
+                 concat=False, device="cuda", **kwargs):
+        super(MeanAggregator, self).__init__(**kwargs)
+        self.dropout = dropout
+        self.bias = bias
+        self.act = act
+        self.concat = concat
+        if neigh_input_dim is None:
+            neigh_input_dim = input_dim
+        self.vars["neigh_weights"] = glorot([neigh_input_dim, output_dim], name="neigh_weights", device=device)
+        self.vars["self_weights"] = glorot([input_dim, output_dim], name="self_weights", device=device)
+        if self.bias:   # the reference dereferences self.output_dim too early here (aggregators.py:34-35); fixed, not replicated
+            self.vars["bias"] = zeros([output_dim * (2 if concat else 1)], name="bias", device=device)
+        self.input_dim = input_dim
+        self.output_dim = output_dim
+        self.neigh_input_dim = neigh_input_dim
+        self.math = _DEFAULT_MATH[0]
+
+    def _combine(self):
+        return ops.COMBINE_CONCAT if self.concat else ops.COMBINE_ADD
+
+    def _call(self, inputs):
+        self_vecs, neigh_vecs = inputs
+        n, k, d = neigh_vecs.shape
+        neigh_vecs = _dropout(neigh_vecs, self.dropout)
+        self_vecs = _dropout(self_vecs, self.dropout)
+        _, means = ops.gather_mean(neigh_vecs.reshape(n * k, d), _dense_segment(n, k), want_self=False)
+        return self._finish([(self_vecs, self.input_dim, self.vars["self_weights"]),
+                             (means, self.neigh_input_dim, self.vars["neigh_weights"])], self._combine())
+
+    def aggregate_rows(self, src, segments):
+        if self.dropout:
+            raise NotImplementedError("dropout > 0 uses the dense call path")
+        xs, xm = ops.gather_mean(src, segments, want_self=True)
+        return self._finish([(xs, self.input_dim, self.vars["self_weights"]),
+                             (xm, self.neigh_input_dim, self.vars["neigh_weights"])], self._combine())
+
+
+class GCNAggregator(_SageAggregator):
+    """act(mean_{k+1}(neigh U self) @ weights) - aggregators.py:101-116 (single weight, concat ignored)."""
+
+    def __init__(self, input_dim, output_dim, neigh_input_dim=None, dropout=0., bias=False, act=relu, name=None,
+                 concat=False, device="cuda", **kwargs):
+        super(GCNAggregator, self).__init__(**kwargs)
+        self.dropout = dropout
+        self.bias = bias
+        self.act = act
+        self.concat = concat
+        if neigh_input_dim is None:
+            neigh_input_dim = input_dim
+        self.vars["weights"] = glorot([neigh_input_dim, output_dim], name="neigh_weights", device=device)
+        if self.bias:
+            self.vars["bias"] = zeros([output_dim], name="bias", device=device)
+        self.input_dim = input_dim
+        self.output_dim = output_dim
+        self.neigh_input_dim = neigh_input_dim
+        self.math = _DEFAULT_MATH[0]
+
+    def _call(self, inputs):
+        self_vecs, neigh_vecs = inputs
+        n, k, d = neigh_vecs.shape
+        if self_vecs.shape[1] != d:
+            raise ValueError("GCNAggregator needs self and neighbour vectors of equal width")
+        neigh_vecs = _dropout(neigh_vecs, self.dropout)
+        self_vecs = _dropout(self_vecs, self.dropout)
+        # one source matrix: neighbours first, then the self rows
+        src = torch.cat([neigh_vecs.reshape(n * k, d), self_vecs], dim=0)
+        seg = [ops.make_segment(n, k, self_row0=n * k, neigh_row0=0)]
+        _, means = ops.gather_mean(src, seg, include_self=True, want_self=False)
+        return self._finish([(means, self.neigh_input_dim, self.vars["weights"])], ops.COMBINE_ADD)
+
+    def aggregate_rows(self, src, segments):
+        if self.dropout:
+            raise NotImplementedError("dropout > 0 uses the dense call path")
+        _, means = ops.gather_mean(src, segments, include_self=True, want_self=False)
+        return self._finish([(means, self.neigh_input_dim, self.vars["weights"])], ops.COMBINE_ADD)
+
+
+class MaxPoolingAggregator(_SageAggregator):
+    """act(concat_or_add(self @ Ws, max_k(relu(neigh @ Wm + bm)) @ Wn)) - aggregators.py:119-195,
+    with Dense (layers.py:73-116) as the single MLP layer; hidden 512 ("small") / 1024 ("big")."""
+
+    def __init__(self, input_dim, output_dim, model_size="small", neigh_input_dim=None, dropout=0., bias=False,
+                 act=relu, name=None, concat=False, device="cuda", **kwargs):
+        super(MaxPoolingAggregator, self).__init__(**kwargs)
+        self.dropout = dropout
+        self.bias = bias
+        self.act = act
+        self.concat = concat
+        if neigh_input_dim is None:
+            neigh_input_dim = input_dim
+        if model_size == "small":
+            hidden_dim = self.hidden_dim = 512
+        elif model_size == "big":
+            hidden_dim = self.hidden_dim = 1024
+        else:
+            raise ValueError("model_size must be 'small' or 'big'")
+        self.math = _DEFAULT_MATH[0]
+        self.mlp_layers = [Dense(input_dim=neigh_input_dim, output_dim=hidden_dim, act=relu, dropout=dropout,
+                                 sparse_inputs=False, logging=self.logging, device=device, math=self.math)]
+        self.vars["neigh_weights"] = glorot([hidden_dim, output_dim], name="neigh_weights", device=device)
+        self.vars["self_weights"] = glorot([input_dim, output_dim], name="self_weights", device=device)
+        if self.bias:
+            self.vars["bias"] = zeros([output_dim * (2 if concat else 1)], name="bias", device=device)
+        self.input_dim = input_dim
+        self.output_dim = output_dim
+        self.neigh_input_dim = neigh_input_dim
+
+    def _combine(self):
+        return ops.COMBINE_CONCAT if self.concat else ops.COMBINE_ADD
+
+    def _pool(self, rows, n, k):
+        h = rows
+        for layer in self.mlp_layers:
+            layer.math = self.math
+            h = layer(h)
+        return ops.segment_max(h, n, k)
+
+    def _call(self, inputs):
+        self_vecs, neigh_vecs = inputs
+        n, k, d = neigh_vecs.shape
+        hmax = self._pool(neigh_vecs.reshape(n * k, d), n, k)
+        return self._finish([(self_vecs, self.input_dim, self.vars["self_weights"]),
+                             (hmax, self.hidden_dim, self.vars["neigh_weights"])], self._combine())
+
+    def aggregate_rows(self, src, segments):
+        rows = max(s.out_row0 + s.n for s in segments)
+        dev = src.device
+        xs = torch.empty((rows, src.shape[1]), dtype=torch.float32, device=dev)
+        hmax = torch.empty((rows, self.hidden_dim), dtype=torch.float32, device=dev)
+        for s in segments:
+            n, k = s.n, s.k
+            if s.neigh_ids is not None:
+                nrows = ops.gather_rows(src, s.neigh_ids[:n * k])
+            else:
+                nrows = src[s.neigh_row0:s.neigh_row0 + n * k]
+            hmax[s.out_row0:s.out_row0 + n] = self._pool(nrows, n, k)
+            if s.self_ids is not None:
+                ops.gather_rows(src, s.self_ids[:n], out=xs[s.out_row0:s.out_row0 + n])
+            else:
+                xs[s.out_row0:s.out_row0 + n] = src[s.self_row0:s.self_row0 + n]
+        return self._finish([(xs, self.input_dim, self.vars["self_weights"]),
+                             (hmax, self.hidden_dim, self.vars["neigh_weights"])], self._combine())

@@ -1,0 +1,408 @@
+// K2 / K3a: K-hop feature-row gather and the fused gather + fixed-fanout segmented mean.
+//   reference: tf.nn.embedding_lookup(features, samples[h])      graphsage/models.py:299
+//              tf.reduce_mean(neigh_vecs, axis=1)                graphsage/aggregators.py:48
+//              mean(concat([neigh, self]), 1)  (GCN)             graphsage/aggregators.py:106-107
+//              tf.reduce_max(neigh_h, axis=1)                    graphsage/aggregators.py:182
+//              tf.nn.l2_normalize(x, 1)                          graphsage/models.py:368
+// HBM-bound byte movement: rows are 2.4 KB (F=602 fp32), fetched whole.  Two data paths:
+//   variant 1 (default when rows are 16-B multiples): the TMA bulk-copy engine
+//     (cp.async.bulk global->shared, mbarrier complete_tx) stages whole rows in shared memory;
+//   variant 0: 128-bit ld.global.nc loads, k independent loads in flight per thread.
+#include "common.cuh"
+
+namespace gs {
+
+struct SegTable {
+  gs_segment s[GS_MAX_SEGMENTS];
+  int32_t n_segments;
+  int64_t total_rows;
+};
+
+__device__ __forceinline__ int find_segment(const SegTable& t, int64_t r, int64_t& local) {
+  int si = 0;
+  int64_t base = 0;
+#pragma unroll
+  for (int q = 0; q < GS_MAX_SEGMENTS - 1; ++q) {
+    if (q < t.n_segments - 1 && r >= base + t.s[q].n) {
+      base += t.s[q].n;
+      si = q + 1;
+    }
+  }
+  local = r - base;
+  return si;
+}
+
+__device__ __forceinline__ int64_t clamp_row(int64_t id, int64_t n_rows) {
+  return (id < 0 || id >= n_rows) ? n_rows - 1 : id;
+}
+
+__device__ __forceinline__ float4 mask_tail(float4 v, int col0, int F) {
+  if (col0 + 1 >= F) v.y = 0.f;
+  if (col0 + 2 >= F) v.z = 0.f;
+  if (col0 + 3 >= F) v.w = 0.f;
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// gather + mean, LDG variant.  One block per output row (grid-stride); thread c owns float4
+// column c; the k neighbour rows are summed in j order with kUnroll loads in flight.
+// ------------------------------------------------------------------------------------------
+template <int kUnroll>
+__global__ void __launch_bounds__(256) gather_mean_ldg_kernel(const float* __restrict__ src, int64_t n_src_rows, int F,
+                                                              int64_t pitch, const __grid_constant__ SegTable tab, int include_self,
+                                                              float* __restrict__ out_self,
+                                                              float* __restrict__ out_mean, int64_t out_pitch) {
+  const int ncol4 = (int)(out_pitch >> 2);
+  for (int64_t r = blockIdx.x; r < tab.total_rows; r += gridDim.x) {
+    int64_t i;
+    const gs_segment& sg = tab.s[find_segment(tab, r, i)];
+    const int k = sg.k;
+    const int64_t orow = sg.out_row0 + i;
+    const int64_t srow = clamp_row(sg.self_ids ? (int64_t)sg.self_ids[i] : sg.self_row0 + i, n_src_rows);
+    for (int c = threadIdx.x; c < ncol4; c += blockDim.x) {
+      const int col0 = c * 4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 sv = acc;
+      if (col0 < F) {
+        int j = 0;
+        for (; j + kUnroll <= k; j += kUnroll) {
+          float4 v[kUnroll];
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            int64_t nr = clamp_row(sg.neigh_ids ? (int64_t)sg.neigh_ids[i * k + j + u] : sg.neigh_row0 + i * k + j + u,
+                                   n_src_rows);
+            v[u] = ldg_nc_f4(reinterpret_cast<const float4*>(src + nr * pitch) + c);
+          }
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+          }
+        }
+        for (; j < k; ++j) {
+          int64_t nr = clamp_row(sg.neigh_ids ? (int64_t)sg.neigh_ids[i * k + j] : sg.neigh_row0 + i * k + j, n_src_rows);
+          float4 v = ldg_nc_f4(reinterpret_cast<const float4*>(src + nr * pitch) + c);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        if (include_self || out_self) sv = ldg_nc_f4(reinterpret_cast<const float4*>(src + srow * pitch) + c);
+        float div = (float)(k + (include_self ? 1 : 0));
+        if (include_self) { acc.x += sv.x; acc.y += sv.y; acc.z += sv.z; acc.w += sv.w; }
+        acc.x /= div; acc.y /= div; acc.z /= div; acc.w /= div;
+        acc = mask_tail(acc, col0, F);
+        sv = mask_tail(sv, col0, F);
+      }
+      reinterpret_cast<float4*>(out_mean + orow * out_pitch)[c] = acc;
+      if (out_self) reinterpret_cast<float4*>(out_self + orow * out_pitch)[c] = sv;
+    }
+  }
+}
+
+// scalar fallback for tables whose pitch / alignment rules out 128-bit access
+__global__ void __launch_bounds__(256) gather_mean_scalar_kernel(const float* __restrict__ src, int64_t n_src_rows, int F,
+                                                                 int64_t pitch, const __grid_constant__ SegTable tab, int include_self,
+                                                                 float* __restrict__ out_self,
+                                                                 float* __restrict__ out_mean, int64_t out_pitch) {
+  for (int64_t r = blockIdx.x; r < tab.total_rows; r += gridDim.x) {
+    int64_t i;
+    const gs_segment& sg = tab.s[find_segment(tab, r, i)];
+    const int k = sg.k;
+    const int64_t orow = sg.out_row0 + i;
+    const int64_t srow = clamp_row(sg.self_ids ? (int64_t)sg.self_ids[i] : sg.self_row0 + i, n_src_rows);
+    for (int c = threadIdx.x; c < (int)out_pitch; c += blockDim.x) {
+      float acc = 0.f, sv = 0.f;
+      if (c < F) {
+        for (int j = 0; j < k; ++j) {
+          int64_t nr = clamp_row(sg.neigh_ids ? (int64_t)sg.neigh_ids[i * k + j] : sg.neigh_row0 + i * k + j, n_src_rows);
+          acc += src[nr * pitch + c];
+        }
+        sv = src[srow * pitch + c];
+        if (include_self) acc += sv;
+        acc /= (float)(k + (include_self ? 1 : 0));
+      }
+      out_mean[orow * out_pitch + c] = acc;
+      if (out_self) out_self[orow * out_pitch + c] = sv;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// gather + mean, TMA bulk variant.  Per output row, one elected thread posts k+1 whole-row
+// bulk copies (UBLKCP) into shared memory against one mbarrier; the block then sums the rows
+// column-parallel out of shared memory.  Several CTAs are resident per SM so one CTA's
+// reduction overlaps the others' copies (row buffers of all resident CTAs = bytes in flight).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192) gather_mean_tma_kernel(const float* __restrict__ src, int64_t n_src_rows, int F,
+                                                              int64_t pitch, const __grid_constant__ SegTable tab, int include_self,
+                                                              float* __restrict__ out_self,
+                                                              float* __restrict__ out_mean, int64_t out_pitch,
+                                                              int row_bytes) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int ncol4 = (int)(out_pitch >> 2);
+  const int row_f4 = row_bytes >> 4;
+  uint32_t phase = 0;
+  for (int64_t r = blockIdx.x; r < tab.total_rows; r += gridDim.x) {
+    int64_t i;
+    const gs_segment& sg = tab.s[find_segment(tab, r, i)];
+    const int k = sg.k;
+    const int64_t orow = sg.out_row0 + i;
+    if (threadIdx.x < 32) {
+      // warp 0 posts the copies: lane l takes rows l, l+32, ... (row k = self)
+      if (threadIdx.x == 0) mbar_expect_tx(&bar, (uint32_t)((k + 1) * row_bytes));
+      __syncwarp();
+      for (int j = threadIdx.x; j <= k; j += 32) {
+        int64_t id;
+        if (j < k) id = sg.neigh_ids ? (int64_t)sg.neigh_ids[i * k + j] : sg.neigh_row0 + i * k + j;
+        else id = sg.self_ids ? (int64_t)sg.self_ids[i] : sg.self_row0 + i;
+        id = clamp_row(id, n_src_rows);
+        bulk_g2s(smem + (size_t)j * row_bytes, src + id * pitch, (uint32_t)row_bytes, &bar);
+      }
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1u;
+    const float4* rows = reinterpret_cast<const float4*>(smem);
+    for (int c = threadIdx.x; c < ncol4; c += blockDim.x) {
+      const int col0 = c * 4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 sv = acc;
+      if (col0 < F) {
+#pragma unroll 5
+        for (int j = 0; j < k; ++j) {
+          float4 v = rows[j * row_f4 + c];
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        sv = rows[k * row_f4 + c];
+        float div = (float)(k + (include_self ? 1 : 0));
+        if (include_self) { acc.x += sv.x; acc.y += sv.y; acc.z += sv.z; acc.w += sv.w; }
+        acc.x /= div; acc.y /= div; acc.z /= div; acc.w /= div;
+        acc = mask_tail(acc, col0, F);
+        sv = mask_tail(sv, col0, F);
+      }
+      reinterpret_cast<float4*>(out_mean + orow * out_pitch)[c] = acc;
+      if (out_self) reinterpret_cast<float4*>(out_self + orow * out_pitch)[c] = sv;
+    }
+    __syncthreads();  // all generic-proxy reads of the row buffer are done before it is refilled
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// plain row gather.  TMA variant: each lane of a one-warp CTA moves one row
+// global -> shared -> global entirely with the bulk-copy engine (no register traffic).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) gather_rows_tma_kernel(const unsigned char* __restrict__ src, int64_t n_rows,
+                                                             int64_t pitch_bytes, const int32_t* __restrict__ ids,
+                                                             int64_t n, unsigned char* __restrict__ out,
+                                                             int64_t out_pitch_bytes, int row_bytes) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  const int lane = threadIdx.x;
+  if (lane == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  uint32_t phase = 0;
+  for (int64_t base = (int64_t)blockIdx.x * 32; base < n; base += (int64_t)gridDim.x * 32) {
+    int cnt = (int)((n - base) < 32 ? (n - base) : 32);
+    if (lane == 0) mbar_expect_tx(&bar, (uint32_t)(cnt * row_bytes));
+    __syncwarp();
+    if (lane < cnt) {
+      int64_t id = clamp_row(ids[base + lane], n_rows);
+      bulk_g2s(smem + (size_t)lane * row_bytes, src + id * pitch_bytes, (uint32_t)row_bytes, &bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1u;
+    if (lane < cnt) bulk_s2g(out + (base + lane) * out_pitch_bytes, smem + (size_t)lane * row_bytes, (uint32_t)row_bytes);
+    bulk_commit();
+    bulk_wait_read<0>();  // shared buffer may be overwritten once the stores have read it
+    __syncwarp();
+  }
+  bulk_wait<0>();
+}
+
+// generic byte-row gather (any alignment): one warp per row, 4-byte or 2-byte units
+template <typename T>
+__global__ void __launch_bounds__(256) gather_rows_simple_kernel(const T* __restrict__ src, int64_t n_rows, int F,
+                                                                 int64_t pitch, const int32_t* __restrict__ ids,
+                                                                 int64_t n, T* __restrict__ out, int64_t out_pitch) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    int64_t id = clamp_row(ids[i], n_rows);
+    for (int c = lane; c < F; c += 32) out[i * out_pitch + c] = src[id * pitch + c];
+  }
+}
+
+__global__ void __launch_bounds__(256) segment_max_kernel(const float* __restrict__ x, int64_t n, int k, int C,
+                                                          int64_t ldx, float* __restrict__ out, int64_t ldo) {
+  for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float m = x[(i * k) * ldx + c];
+      for (int j = 1; j < k; ++j) m = fmaxf(m, x[(i * k + j) * ldx + c]);
+      out[i * ldo + c] = m;
+    }
+  }
+}
+
+// one warp per row: x *= rsqrt(max(sum x^2, 1e-12))
+__global__ void __launch_bounds__(256) l2_normalize_kernel(float* __restrict__ x, int64_t n, int C, int64_t ldx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      float v = x[i * ldx + c];
+      ss += v * v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    float inv = 1.0f / sqrtf(fmaxf(ss, 1e-12f));
+    for (int c = lane; c < C; c += 32) x[i * ldx + c] *= inv;
+  }
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace gs
+
+extern "C" {
+
+int32_t gs_gather_rows(const void* feats, int32_t dtype, int64_t n_rows, int32_t F, int64_t pitch, const int32_t* ids,
+                       int64_t n, void* out, int64_t out_pitch, void* stream) {
+  GS_REQUIRE(n >= 0 && F >= 0, "gs_gather_rows: negative size");
+  if (n == 0 || F == 0) return GS_OK;
+  GS_REQUIRE(feats && ids && out, "gs_gather_rows: NULL pointer");
+  GS_REQUIRE(dtype == GS_F32 || dtype == GS_BF16, "gs_gather_rows: dtype %d", dtype);
+  GS_REQUIRE(n_rows > 0 && pitch >= F && out_pitch >= F, "gs_gather_rows: pitch < F");
+  const int es = dtype == GS_F32 ? 4 : 2;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int row_bytes = ((F * es + 15) / 16) * 16;
+  const bool tma_ok = gs::aligned16(feats) && gs::aligned16(out) && (pitch * es) % 16 == 0 && (out_pitch * es) % 16 == 0 &&
+                      row_bytes <= pitch * es && row_bytes <= out_pitch * es && row_bytes * 32 <= 200 * 1024;
+  if (tma_ok && gs::tuning("gather_variant", 1) == 1) {
+    size_t smem = (size_t)row_bytes * 32;
+    static bool attr_set = false;
+    if (!attr_set) {
+      GS_CUDA(cudaFuncSetAttribute(gs::gather_rows_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 16) per_sm = 16;
+    int64_t blocks = (n + 31) / 32;
+    int64_t cap = (int64_t)gs::sm_count() * per_sm;
+    if (blocks > cap) blocks = cap;
+    gs::gather_rows_tma_kernel<<<(unsigned)blocks, 32, smem, st>>>((const unsigned char*)feats, n_rows, pitch * es, ids, n,
+                                                                   (unsigned char*)out, out_pitch * es, row_bytes);
+    return gs::launch_check("gather_rows_tma_kernel");
+  }
+  int64_t blocks = (n + 7) / 8;
+  int64_t cap = (int64_t)gs::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (dtype == GS_F32)
+    gs::gather_rows_simple_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)feats, n_rows, F, pitch, ids, n,
+                                                                           (float*)out, out_pitch);
+  else
+    gs::gather_rows_simple_kernel<uint16_t><<<(unsigned)blocks, 256, 0, st>>>((const uint16_t*)feats, n_rows, F, pitch, ids,
+                                                                              n, (uint16_t*)out, out_pitch);
+  return gs::launch_check("gather_rows_simple_kernel");
+}
+
+int32_t gs_gather_mean(const void* src, int32_t dtype, int64_t n_src_rows, int32_t F, int64_t pitch,
+                       const gs_segment* segments_host, int32_t n_segments, int32_t include_self, void* out_self,
+                       void* out_mean, int64_t out_pitch, void* stream) {
+  GS_REQUIRE(dtype == GS_F32, "gs_gather_mean: only GS_F32 is implemented (dtype=%d)", dtype);
+  GS_REQUIRE(n_segments >= 0 && n_segments <= GS_MAX_SEGMENTS, "gs_gather_mean: n_segments=%d (max %d)", n_segments,
+             GS_MAX_SEGMENTS);
+  GS_REQUIRE(segments_host || n_segments == 0, "gs_gather_mean: segments_host is NULL");
+  gs::SegTable tab;
+  memset(&tab, 0, sizeof(tab));
+  tab.n_segments = n_segments;
+  int kmax = 0;
+  for (int s = 0; s < n_segments; ++s) {
+    tab.s[s] = segments_host[s];
+    GS_REQUIRE(tab.s[s].n >= 0 && tab.s[s].k >= 1, "gs_gather_mean: segment %d has n=%lld k=%d", s, (long long)tab.s[s].n,
+               tab.s[s].k);
+    tab.total_rows += tab.s[s].n;
+    if (tab.s[s].k > kmax) kmax = tab.s[s].k;
+  }
+  if (tab.total_rows == 0) return GS_OK;
+  GS_REQUIRE(src && out_mean, "gs_gather_mean: NULL pointer");
+  GS_REQUIRE(F > 0 && pitch >= F && out_pitch >= F && n_src_rows > 0, "gs_gather_mean: bad F/pitch");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* fsrc = (const float*)src;
+  const bool vec_ok = gs::aligned16(src) && gs::aligned16(out_mean) && (!out_self || gs::aligned16(out_self)) &&
+                      pitch % 4 == 0 && out_pitch % 4 == 0 && ((F + 3) / 4) * 4 <= pitch;
+  if (!vec_ok) {
+    int64_t blocks = tab.total_rows;
+    int64_t cap = (int64_t)gs::sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    gs::gather_mean_scalar_kernel<<<(unsigned)blocks, 256, 0, st>>>(fsrc, n_src_rows, F, pitch, tab, include_self,
+                                                                    (float*)out_self, (float*)out_mean, out_pitch);
+    return gs::launch_check("gather_mean_scalar_kernel");
+  }
+  const int ncol4 = (int)(out_pitch / 4);
+  const int row_bytes = ((F + 3) / 4) * 16;
+  const size_t smem = (size_t)row_bytes * (kmax + 1);
+  const int variant = gs::tuning("gather_variant", 1);
+  if (variant == 1 && smem <= 200 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      GS_CUDA(cudaFuncSetAttribute(gs::gather_mean_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    int threads = ((ncol4 + 31) / 32) * 32;
+    if (threads > 192) threads = 192;
+    if (threads < 32) threads = 32;
+    int per_sm = (int)((224 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    int lim = gs::tuning("gather_ctas_per_sm", 8);
+    if (per_sm > lim) per_sm = lim;
+    int64_t blocks = tab.total_rows;
+    int64_t cap = (int64_t)gs::sm_count() * per_sm;
+    if (blocks > cap) blocks = cap;
+    gs::gather_mean_tma_kernel<<<(unsigned)blocks, threads, smem, st>>>(fsrc, n_src_rows, F, pitch, tab, include_self,
+                                                                        (float*)out_self, (float*)out_mean, out_pitch,
+                                                                        row_bytes);
+    return gs::launch_check("gather_mean_tma_kernel");
+  }
+  int threads = ((ncol4 + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  int64_t blocks = tab.total_rows;
+  int64_t cap = (int64_t)gs::sm_count() * gs::tuning("gather_ctas_per_sm", 8);
+  if (blocks > cap) blocks = cap;
+  gs::gather_mean_ldg_kernel<5><<<(unsigned)blocks, threads, 0, st>>>(fsrc, n_src_rows, F, pitch, tab, include_self,
+                                                                      (float*)out_self, (float*)out_mean, out_pitch);
+  return gs::launch_check("gather_mean_ldg_kernel");
+}
+
+int32_t gs_segment_max(const float* x, int64_t n, int32_t k, int32_t C, int64_t ldx, float* out, int64_t ldo,
+                       void* stream) {
+  GS_REQUIRE(n >= 0 && k >= 1 && C >= 0, "gs_segment_max: bad sizes");
+  if (n == 0 || C == 0) return GS_OK;
+  GS_REQUIRE(x && out, "gs_segment_max: NULL pointer");
+  int64_t blocks = n;
+  int64_t cap = (int64_t)gs::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  gs::segment_max_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, k, C, ldx, out, ldo);
+  return gs::launch_check("segment_max_kernel");
+}
+
+int32_t gs_l2_normalize_rows(float* x, int64_t n, int32_t C, int64_t ldx, void* stream) {
+  GS_REQUIRE(n >= 0 && C >= 0, "gs_l2_normalize_rows: bad sizes");
+  if (n == 0 || C == 0) return GS_OK;
+  GS_REQUIRE(x, "gs_l2_normalize_rows: NULL pointer");
+  int64_t blocks = (n + 7) / 8;
+  int64_t cap = (int64_t)gs::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  gs::l2_normalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, C, ldx);
+  return gs::launch_check("l2_normalize_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+// K1: UniformNeighborSampler kernels.
+//   padded mode  - reference graphsage/neigh_samplers.py:24-29 (one shared column permutation per call)
+//   CSR mode     - warp-per-node per-node draws (north_star), semantics in oracle/sampler.py
+#include "common.cuh"
+
+namespace gs {
+
+constexpr int kMaxDegSmem = 1024;  // permutation scratch (int16 entries) lives in static smem
+
+// Each block recomputes the k-step Fisher-Yates prefix in shared memory (k <= 32 steps of a
+// serial swap chain - ~1 us, cheaper than a separate launch), then threads stream
+// out[i*k + j] = adj[ids[i]*MD + pi[j]].  Integer/byte work: bound by the 4-byte random reads
+// of the adj table (k sectors per node), not by anything a tensor core could help with.
+__global__ void __launch_bounds__(256) sample_padded_kernel(const int32_t* __restrict__ adj, int64_t n_rows,
+                                                            int32_t max_deg, const int32_t* __restrict__ ids,
+                                                            int64_t n, int32_t k,
+                                                            const int32_t* __restrict__ col_perm, uint64_t seed,
+                                                            uint64_t counter, const uint64_t* __restrict__ counter_dev,
+                                                            int32_t* __restrict__ out) {
+  __shared__ int16_t perm[kMaxDegSmem];
+  __shared__ int32_t pi[kMaxDegSmem];
+  if (col_perm != nullptr) {
+    for (int j = threadIdx.x; j < k; j += blockDim.x) pi[j] = col_perm[j];
+  } else {
+    for (int j = threadIdx.x; j < max_deg; j += blockDim.x) perm[j] = (int16_t)j;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint64_t ctr = counter + (counter_dev ? *counter_dev : 0ull);
+      u32x4 r{0, 0, 0, 0};
+      for (int i = 0; i < k; ++i) {
+        if ((i & 3) == 0) {
+          u32x4 c{(uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)(i >> 2), kStreamPadded};
+          r = philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        }
+        int j = i + (int)mulhi32(pick(r, i & 3), (uint32_t)(max_deg - i));
+        int16_t t = perm[i];
+        perm[i] = perm[j];
+        perm[j] = t;
+        pi[i] = perm[i];
+      }
+    }
+  }
+  __syncthreads();
+  const int64_t total = n * (int64_t)k;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i = e / k;
+    int j = (int)(e - i * k);
+    int64_t id = ids[i];
+    if (id < 0 || id >= n_rows) id = n_rows - 1;  // out-of-range -> dummy row (TF GPU gather would return zeros)
+    out[e] = adj[id * max_deg + pi[j]];
+  }
+}
+
+// One warp per requested node; lane j owns draw j (k <= 32).
+__global__ void __launch_bounds__(256) sample_csr_kernel(const int64_t* __restrict__ indptr,
+                                                         const int32_t* __restrict__ indices, int64_t n_nodes,
+                                                         const int32_t* __restrict__ ids, int64_t n, int32_t k,
+                                                         int32_t replace_if_short, uint64_t seed, uint64_t counter,
+                                                         const uint64_t* __restrict__ counter_dev, int32_t pad_id,
+                                                         int32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const uint64_t ctr = counter + (counter_dev ? *counter_dev : 0ull);
+  for (int64_t t = warp; t < n; t += nwarps) {
+    int64_t id = ids[t];
+    int64_t start = 0, deg = 0;
+    if (id >= 0 && id < n_nodes) {
+      start = indptr[id];
+      deg = indptr[id + 1] - start;
+    }
+    int32_t res = pad_id;
+    uint32_t r = 0;
+    if (lane < k && deg > 0) r = philox_draw(seed, ctr, (uint32_t)t, kStreamCsr, lane);
+    if (deg >= k) {
+      // Floyd: step j draws from [0, deg-k+j]; a repeat is replaced by deg-k+j itself
+      int64_t mine = -1;
+      for (int j = 0; j < k; ++j) {
+        uint32_t rj = __shfl_sync(0xffffffffu, r, j);
+        int64_t m = deg - k + j;
+        int64_t tpos = (int64_t)mulhi32(rj, (uint32_t)(m + 1));
+        unsigned dup = __ballot_sync(0xffffffffu, lane < j && mine == tpos);
+        if (lane == j) mine = dup ? m : tpos;
+      }
+      if (lane < k) res = indices[start + mine];
+    } else if (deg > 0) {
+      if (replace_if_short) {
+        if (lane < k) res = indices[start + (int64_t)mulhi32(r, (uint32_t)deg)];
+      } else {
+        if (lane < deg) res = indices[start + lane];
+      }
+    }
+    if (lane < k) out[t * k + lane] = res;
+  }
+}
+
+}  // namespace gs
+
+extern "C" {
+
+int32_t gs_sample_padded(const int32_t* adj, int64_t n_rows, int32_t max_deg, const int32_t* ids, int64_t n, int32_t k,
+                         const int32_t* col_perm, uint64_t seed, uint64_t counter, const uint64_t* counter_dev,
+                         int32_t* out, void* stream) {
+  GS_REQUIRE(n >= 0 && k >= 0, "gs_sample_padded: negative size (n=%lld, k=%d)", (long long)n, k);
+  if (n == 0 || k == 0) return GS_OK;
+  GS_REQUIRE(adj && ids && out, "gs_sample_padded: NULL pointer");
+  GS_REQUIRE(n_rows > 0 && max_deg > 0 && max_deg <= gs::kMaxDegSmem, "gs_sample_padded: need 0 < max_deg <= %d (got %d)",
+             gs::kMaxDegSmem, max_deg);
+  GS_REQUIRE(k <= max_deg, "gs_sample_padded: num_samples %d > max_degree %d", k, max_deg);
+  int64_t total = n * (int64_t)k;
+  int64_t blocks = (total + 255) / 256;
+  int64_t cap = (int64_t)gs::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  gs::sample_padded_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(adj, n_rows, max_deg, ids, n, k, col_perm,
+                                                                               seed, counter, counter_dev, out);
+  return gs::launch_check("sample_padded_kernel");
+}
+
+int32_t gs_sample_csr(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, const int32_t* ids, int64_t n,
+                      int32_t k, int32_t replace_if_short, uint64_t seed, uint64_t counter, const uint64_t* counter_dev,
+                      int32_t pad_id, int32_t* out, void* stream) {
+  GS_REQUIRE(n >= 0 && k >= 0, "gs_sample_csr: negative size");
+  if (n == 0 || k == 0) return GS_OK;
+  GS_REQUIRE(indptr && indices && ids && out, "gs_sample_csr: NULL pointer");
+  if (k > 32) {
+    gs::set_error("gs_sample_csr: k=%d > 32 not supported (one lane per draw)", k);
+    return GS_ERR_UNSUPPORTED;
+  }
+  int64_t blocks = (n + 7) / 8;  // 8 warps per block
+  int64_t cap = (int64_t)gs::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  gs::sample_csr_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(indptr, indices, n_nodes, ids, n, k,
+                                                                            replace_if_short, seed, counter, counter_dev,
+                                                                            pad_id, out);
+  return gs::launch_check("sample_csr_kernel");
+}
+
+}  // extern "C"

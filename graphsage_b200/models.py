@@ -1,0 +1,153 @@
+"""SAGEInfo and SampleAndAggregate.sample / .aggregate - the surface of reference
+graphsage/models.py:178-330 over the B200 kernels.
+
+The TF placeholders / FLAGS the reference threads through become explicit arguments:
+`placeholders` is a plain dict ({"batch_size": int, "dropout": float, ...}).
+"""
+from collections import namedtuple
+
+import torch
+
+from . import ops
+from .aggregators import GCNAggregator, MaxPoolingAggregator, MeanAggregator
+from .layers import identity, relu  # noqa: F401
+
+# reference graphsage/models.py:180-185
+SAGEInfo = namedtuple("SAGEInfo",
+                      ["layer_name",      # name of the layer (always "node"; unused)
+                       "neigh_sampler",   # callable neigh_sampler
+                       "num_samples",
+                       "output_dim"])     # the output (i.e., hidden) dimension
+
+_AGGREGATORS = {"mean": MeanAggregator, "maxpool": MaxPoolingAggregator, "gcn": GCNAggregator}
+
+
+class SampleAndAggregate(object):
+    """The sample -> K-hop gather -> aggregate recursion of GraphSAGE (reference models.py:187-330).
+
+    features : float32 CUDA tensor [N+1, F] whose LAST row is the all-zero dummy row
+               (reference supervised_train.py:133-135), or a numpy array (uploaded, dummy row NOT added).
+    adj      : int32 CUDA tensor [N+1, max_degree] padded adjacency (reference minibatch.py:227-245).
+    """
+
+    def __init__(self, placeholders, features, adj, degrees, layer_infos, concat=True, aggregator_type="mean",
+                 model_size="small", identity_dim=0, device="cuda", **kwargs):
+        allowed_kwargs = {"name", "logging", "model_size"}
+        for kwarg in kwargs.keys():
+            assert kwarg in allowed_kwargs, "Invalid keyword argument: " + kwarg   # reference models.py:22-24
+        if aggregator_type not in _AGGREGATORS:
+            if aggregator_type in ("seq", "meanpool"):
+                raise NotImplementedError("aggregator_type %r is outside the hot path (SURVEY section 2, row 5)"
+                                          % aggregator_type)
+            raise ValueError("Unknown aggregator: %r" % (aggregator_type,))
+        self.aggregator_cls = _AGGREGATORS[aggregator_type]
+        if identity_dim > 0:
+            raise NotImplementedError("identity_dim > 0 (trainable node embeddings) is out of scope (SURVEY appendix A)")
+        if features is None:
+            raise ValueError("Must have a positive value for identity feature dimension if no input features given.")
+        self.placeholders = placeholders if placeholders is not None else {}
+        self.inputs1 = self.placeholders.get("batch1")
+        self.inputs2 = self.placeholders.get("batch2")
+        self.model_size = model_size
+        self.adj_info = adj
+        if not torch.is_tensor(features):
+            features = torch.as_tensor(features, dtype=torch.float32)
+        self.features = features.to(device=device, dtype=torch.float32).contiguous()
+        self.degrees = degrees
+        self.concat = concat
+        self.dims = [self.features.shape[1] + identity_dim]
+        self.dims.extend([layer_infos[i].output_dim for i in range(len(layer_infos))])   # models.py:244-245
+        self.batch_size = self.placeholders.get("batch_size")
+        self.layer_infos = layer_infos
+        self.device = torch.device(device)
+        self.aggregators = None
+
+    # ------------------------------------------------------------------ models.py:254-275
+    def sample(self, inputs, layer_infos, batch_size=None):
+        """Sample neighbours to be the supportive fields for multi-layer convolutions.
+        Returns (samples, support_sizes); samples[h] is a flat int32 vector of batch*support[h] ids,
+        row-major nested: samples[h+1][i*k + j] is neighbour j of samples[h][i]."""
+        if batch_size is None:
+            batch_size = self.batch_size if self.batch_size is not None else inputs.numel()
+        samples = [inputs.reshape(-1)]
+        support_size = 1
+        support_sizes = [support_size]
+        for k in range(len(layer_infos)):
+            t = len(layer_infos) - k - 1
+            support_size *= layer_infos[t].num_samples
+            sampler = layer_infos[t].neigh_sampler
+            node = sampler((samples[k], layer_infos[t].num_samples))
+            samples.append(node.reshape(support_size * batch_size))
+            support_sizes.append(support_size)
+        return samples, support_sizes
+
+    # ------------------------------------------------------------------ models.py:278-330
+    def aggregate(self, samples, input_features, dims, num_samples, support_sizes, batch_size=None,
+                  aggregators=None, name=None, concat=False, model_size="small"):
+        """At each layer, aggregate hidden representations of neighbours to compute the hidden
+        representations at the next layer.  `input_features` is the feature table [N+1, F] (the
+        reference passes `[self.features]` - a 1-element list - and indexes it implicitly; both forms
+        are accepted).  Returns (hidden[0] of shape [batch, out_w], aggregators)."""
+        if batch_size is None:
+            batch_size = self.batch_size if self.batch_size is not None else samples[0].numel()
+        feats = input_features[0] if isinstance(input_features, (list, tuple)) else input_features
+        L = len(num_samples)
+        new_agg = aggregators is None
+        if new_agg:
+            aggregators = []
+            for layer in range(L):
+                dim_mult = 2 if concat and (layer != 0) else 1
+                act = identity if layer == L - 1 else relu                      # models.py:307-310
+                kw = dict(act=act, dropout=self.placeholders.get("dropout", 0.), name=name, concat=concat,
+                          device=self.device)
+                if self.aggregator_cls is MaxPoolingAggregator:
+                    kw["model_size"] = model_size
+                aggregators.append(self.aggregator_cls(dim_mult * dims[layer], dims[layer + 1], **kw))
+        if any(getattr(a, "dropout", 0.) for a in aggregators):
+            return self._aggregate_materialised(samples, feats, dims, num_samples, support_sizes, batch_size,
+                                                aggregators, concat), aggregators
+        # gather-fused recursion: hop h of a layer occupies rows [row0[h], row0[h] + batch*support[h])
+        counts = [batch_size * support_sizes[h] for h in range(L + 1)]
+        src = feats
+        for layer in range(L):
+            hops = L - layer
+            row0 = [sum(counts[:h]) for h in range(hops + 1)]
+            segs = []
+            for hop in range(hops):
+                k = num_samples[L - hop - 1]                                     # models.py:324
+                if layer == 0:
+                    segs.append(ops.Seg(counts[hop], k, self_ids=samples[hop], neigh_ids=samples[hop + 1],
+                                        out_row0=row0[hop]))
+                else:
+                    segs.append(ops.Seg(counts[hop], k, self_row0=row0[hop], neigh_row0=row0[hop + 1],
+                                        out_row0=row0[hop]))
+            src = aggregators[layer].aggregate_rows(src, segs)
+        return src[:counts[0]], aggregators
+
+    def _aggregate_materialised(self, samples, feats, dims, num_samples, support_sizes, batch_size, aggregators,
+                                concat):
+        """The reference's literal recursion (hidden[h] materialised); used when dropout > 0."""
+        hidden = [ops.gather_rows(feats, s) for s in samples]                    # models.py:299
+        L = len(num_samples)
+        for layer in range(L):
+            nxt = []
+            for hop in range(L - layer):
+                d = hidden[hop + 1].shape[1]
+                neigh = hidden[hop + 1].reshape(batch_size * support_sizes[hop], num_samples[L - hop - 1], d)
+                nxt.append(aggregators[layer]((hidden[hop], neigh)))
+            hidden = nxt
+        return hidden[0]
+
+    # ------------------------------------------------------------------ convenience: the whole path
+    def forward(self, batch, normalize=True):
+        """sample -> aggregate -> l2_normalize (reference models.py:347-350, 368) for one id batch."""
+        batch = batch.to(device=self.device, dtype=torch.int32).reshape(-1)
+        n = batch.numel()
+        samples, support = self.sample(batch, self.layer_infos, batch_size=n)
+        num_samples = [info.num_samples for info in self.layer_infos]
+        out, self.aggregators = self.aggregate(samples, [self.features], self.dims, num_samples, support,
+                                               batch_size=n, aggregators=self.aggregators, concat=self.concat,
+                                               model_size=self.model_size)
+        if normalize:
+            out = ops.l2_normalize_rows_(out.contiguous())
+        return out

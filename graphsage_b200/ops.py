@@ -1,0 +1,186 @@
+"""Functional wrappers: torch CUDA tensors in, torch CUDA tensors out, all work done by
+libgraphsage_b200.so on the current CUDA stream.  torch only owns memory and streams here."""
+import torch
+
+from . import _lib
+from ._lib import (ACT_NONE, ACT_RELU, COMBINE_ADD, COMBINE_CONCAT, MATH_FP32_SIMT, MATH_TF32X3, MATH_TF32,
+                   MATH_BF16, GemmPart, Segment, check, lib, ptr, require_cuda, stream_ptr)
+
+_U64 = 2**64 - 1
+
+# optional per-kernel timing (bench.py): name -> list of (start_event, end_event) on the current stream
+PROBE = None
+LAUNCHES = 0          # kernels of ours launched through this module (bench.py reports it as gpu_launches)
+
+
+def _probe(name):
+    if PROBE is None:
+        return None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    PROBE.setdefault(name, []).append((e0, e1))
+    e0.record()
+    return e1
+
+
+def _launched(n=1, ev=None):
+    global LAUNCHES
+    LAUNCHES += n
+    if ev is not None:
+        ev.record()
+
+
+def pad_cols(f):
+    return (int(f) + 7) // 8 * 8
+
+
+def _i32(t, name):
+    if t.dtype != torch.int32:
+        raise TypeError("%s must be int32 (got %s)" % (name, t.dtype))
+    return t.contiguous()
+
+
+def sample_padded(adj, ids, k, seed, counter, col_perm=None, counter_dev=None, out=None):
+    """UniformNeighborSampler._call - reference graphsage/neigh_samplers.py:24-29."""
+    require_cuda(adj, ids, col_perm, counter_dev)
+    adj, ids = _i32(adj, "adj"), _i32(ids.reshape(-1), "ids")
+    n = ids.numel()
+    if out is None:
+        out = torch.empty((n, k), dtype=torch.int32, device=adj.device)
+    ev = _probe("sample_padded")
+    check(lib().gs_sample_padded(ptr(adj), adj.shape[0], adj.shape[1], ptr(ids), n, k, ptr(col_perm), seed & _U64,
+                                 counter & _U64, ptr(counter_dev), ptr(out), stream_ptr()))
+    _launched(1 if n * k else 0, ev)
+    return out
+
+
+def sample_csr(indptr, indices, ids, k, seed, counter, replace_if_short=True, pad_id=-1, counter_dev=None):
+    require_cuda(indptr, indices, ids)
+    if indptr.dtype != torch.int64:
+        raise TypeError("indptr must be int64")
+    indices, ids = _i32(indices, "indices"), _i32(ids.reshape(-1), "ids")
+    n = ids.numel()
+    out = torch.empty((n, k), dtype=torch.int32, device=ids.device)
+    check(lib().gs_sample_csr(ptr(indptr), ptr(indices), indptr.numel() - 1, ptr(ids), n, k, int(bool(replace_if_short)),
+                              seed & _U64, counter & _U64, ptr(counter_dev), pad_id, ptr(out), stream_ptr()))
+    _launched(1 if n * k else 0)
+    return out
+
+
+def _dtype_code(t):
+    if t.dtype == torch.float32:
+        return _lib.GS_F32
+    if t.dtype == torch.bfloat16:
+        return _lib.GS_BF16
+    raise TypeError("features must be float32 or bfloat16 (got %s)" % t.dtype)
+
+
+def gather_rows(feats, ids, out=None):
+    """tf.nn.embedding_lookup(features, ids) - reference graphsage/models.py:299."""
+    require_cuda(feats, ids)
+    if feats.dim() != 2 or feats.stride(1) != 1:
+        raise ValueError("features must be a row-major 2-D tensor")
+    ids = _i32(ids.reshape(-1), "ids")
+    n, F = ids.numel(), feats.shape[1]
+    if out is None:
+        out = torch.empty((n, F), dtype=feats.dtype, device=feats.device)
+    check(lib().gs_gather_rows(ptr(feats), _dtype_code(feats), feats.shape[0], F, feats.stride(0), ptr(ids), n,
+                               ptr(out), out.stride(0), stream_ptr()))
+    _launched(1 if n * F else 0)
+    return out
+
+
+class Seg(object):
+    """One hop's rows for gather_mean: n output rows with fanout k.  Neighbour j of row i is
+    src[neigh_ids[i*k + j]] (or src[neigh_row0 + i*k + j] when neigh_ids is None); the self row is
+    src[self_ids[i]] (or src[self_row0 + i]).  Output row = out_row0 + i."""
+    __slots__ = ("n", "k", "self_ids", "neigh_ids", "self_row0", "neigh_row0", "out_row0")
+
+    def __init__(self, n, k, self_ids=None, neigh_ids=None, self_row0=0, neigh_row0=0, out_row0=0):
+        self.n, self.k = int(n), int(k)
+        self.self_ids = None if self_ids is None else _i32(self_ids.reshape(-1), "self_ids")
+        self.neigh_ids = None if neigh_ids is None else _i32(neigh_ids.reshape(-1), "neigh_ids")
+        self.self_row0, self.neigh_row0, self.out_row0 = int(self_row0), int(neigh_row0), int(out_row0)
+        if self.self_ids is not None and self.self_ids.numel() < self.n:
+            raise ValueError("self_ids shorter than n")
+        if self.neigh_ids is not None and self.neigh_ids.numel() < self.n * self.k:
+            raise ValueError("neigh_ids shorter than n*k")
+
+    def c_struct(self):
+        require_cuda(self.self_ids, self.neigh_ids)
+        return Segment(ptr(self.self_ids), ptr(self.neigh_ids), self.self_row0, self.neigh_row0, self.n, self.k, 0,
+                       self.out_row0)
+
+
+def make_segment(n, k, self_ids=None, neigh_ids=None, self_row0=0, neigh_row0=0, out_row0=0):
+    return Seg(n, k, self_ids, neigh_ids, self_row0, neigh_row0, out_row0)
+
+
+def gather_mean(src, segments, include_self=False, want_self=True, out_pitch=None, out_mean=None, out_self=None):
+    """Fused embedding_lookup + reduce_mean over the fanout (models.py:299 + aggregators.py:48 / :106-107).
+    segments: list of Seg; returns (out_self or None, out_mean), each [rows, out_pitch]."""
+    require_cuda(src)
+    if src.dtype != torch.float32 or src.dim() != 2 or src.stride(1) != 1:
+        raise ValueError("src must be a row-major float32 2-D tensor")
+    F = src.shape[1]
+    if out_pitch is None:
+        out_pitch = pad_cols(F)
+    rows = max([s.out_row0 + s.n for s in segments] + [0])
+    if out_mean is None:
+        out_mean = torch.empty((rows, out_pitch), dtype=torch.float32, device=src.device)
+    if want_self and out_self is None:
+        out_self = torch.empty((rows, out_pitch), dtype=torch.float32, device=src.device)
+    arr = (Segment * max(len(segments), 1))(*[s.c_struct() for s in segments])
+    ev = _probe("gather_mean/%d" % rows)
+    check(lib().gs_gather_mean(ptr(src), _lib.GS_F32, src.shape[0], F, src.stride(0), arr, len(segments),
+                               int(bool(include_self)), ptr(out_self) if want_self else 0, ptr(out_mean), out_pitch,
+                               stream_ptr()))
+    _launched(1 if rows else 0, ev)
+    return (out_self if want_self else None), out_mean
+
+
+def segment_max(x, n, k):
+    require_cuda(x)
+    C = x.shape[1]
+    out = torch.empty((n, C), dtype=torch.float32, device=x.device)
+    check(lib().gs_segment_max(ptr(x), n, k, C, x.stride(0), ptr(out), out.stride(0), stream_ptr()))
+    _launched(1 if n * C else 0)
+    return out
+
+
+def sage_gemm(parts, combine=COMBINE_ADD, bias=None, act=ACT_NONE, math=MATH_FP32_SIMT, out=None):
+    """parts: [(A[M, >=K] (row stride used as lda), K, B[K, N])] (1 or 2).  act(concat_or_add(A_p[:, :K] @ B_p) + bias)."""
+    M = parts[0][0].shape[0]
+    arr = (GemmPart * len(parts))()
+    keep = []
+    for i, (A, K, B) in enumerate(parts):
+        require_cuda(A, B)
+        if A.dtype != torch.float32 or B.dtype != torch.float32:
+            raise TypeError("sage_gemm operands must be float32")
+        if A.stride(1) != 1 or A.shape[0] != M or A.shape[1] < K:
+            raise ValueError("bad A operand for part %d" % i)
+        B = B.contiguous()
+        if B.shape[0] != K:
+            raise ValueError("part %d: B has %d rows, expected K=%d" % (i, B.shape[0], K))
+        keep.append(B)
+        arr[i] = GemmPart(ptr(A), A.stride(0), K, ptr(B), B.stride(0), B.shape[1])
+    ntot = sum(p[2].shape[1] for p in parts) if (combine == COMBINE_CONCAT) else parts[0][2].shape[1]
+    dev = parts[0][0].device
+    if out is None:
+        out = torch.empty((M, ntot), dtype=torch.float32, device=dev)
+    ws_bytes = lib().gs_sage_gemm_workspace_bytes(M, arr, len(parts), math)
+    if ws_bytes < 0:
+        check(-1)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes > 0 else None
+    ev = _probe("sage_gemm/%d" % M)
+    check(lib().gs_sage_gemm(M, arr, len(parts), combine, ptr(bias), act, math, ptr(out), out.stride(0), ptr(ws),
+                             stream_ptr()))
+    _launched(1 if M else 0, ev)
+    return out
+
+
+def l2_normalize_rows_(x):
+    """In-place tf.nn.l2_normalize(x, 1) - reference graphsage/models.py:368."""
+    require_cuda(x)
+    check(lib().gs_l2_normalize_rows(ptr(x), x.shape[0], x.shape[1], x.stride(0), stream_ptr()))
+    _launched(1 if x.numel() else 0)
+    return x

@@ -1,0 +1,51 @@
+"""Synthetic graphs shaped like the reference's datasets (no network, no real data).
+
+reddit_like(): N=232,965 nodes, 41 communities, heavy-tailed degrees (mean ~ 50 undirected
+neighbours before symmetrisation => ~100 after, like Reddit's 11.6 M undirected edges), F=602
+N(0,1) features.  Used by bench.py and the full-size GPU tests (BASELINE.json configs[1..3]).
+"""
+import numpy as np
+
+
+def community_graph_csr(n, n_comm=41, mean_deg=50, p_in=0.8, seed=123, max_deg_cap=2000):
+    """Undirected community-structured graph with a Pareto degree tail, returned as CSR
+    (indptr int64 [n+1], indices int32) over nodes 0..n-1 with sorted, de-duplicated rows."""
+    rs = np.random.RandomState(seed)
+    comm = rs.randint(0, n_comm, size=n).astype(np.int32)
+    order = np.argsort(comm, kind="stable")
+    comm_start = np.searchsorted(comm[order], np.arange(n_comm))
+    comm_size = np.diff(np.append(comm_start, n))
+    # out-degrees: Pareto(alpha=2.2) scaled to the target mean, capped
+    raw = (rs.pareto(2.2, size=n) + 1.0)
+    d = np.minimum(np.maximum((raw * (mean_deg / raw.mean())).astype(np.int64), 1), max_deg_cap)
+    src = np.repeat(np.arange(n, dtype=np.int64), d)
+    m = len(src)
+    inside = rs.random_sample(m) < p_in
+    c = comm[src]
+    dst_in = order[comm_start[c] + (rs.random_sample(m) * comm_size[c]).astype(np.int64)]
+    dst_out = rs.randint(0, n, size=m)
+    dst = np.where(inside, dst_in, dst_out).astype(np.int64)
+    keep = src != dst
+    src, dst = src[keep], dst[keep]
+    a = np.concatenate([src, dst])
+    b = np.concatenate([dst, src])
+    key = a * n + b
+    key.sort()
+    key = key[np.concatenate([[True], key[1:] != key[:-1]])]
+    a, b = key // n, (key % n).astype(np.int32)
+    indptr = np.concatenate([[0], np.cumsum(np.bincount(a, minlength=n))]).astype(np.int64)
+    return indptr, b, comm
+
+
+def reddit_like(n=232965, f=602, max_degree=128, seed=123, with_features=True, mean_deg=50):
+    """Returns dict(indptr, indices, adj[n+1, max_degree] int32, deg, comm, features[n+1, f] fp32 with zero last row)."""
+    from .minibatch import padded_from_csr_fast
+    indptr, indices, comm = community_graph_csr(n, mean_deg=mean_deg, seed=seed)
+    adj, deg = padded_from_csr_fast(indptr, indices, max_degree, seed=seed)
+    out = dict(indptr=indptr, indices=indices, adj=adj, deg=deg, comm=comm, n=n, f=f, max_degree=max_degree)
+    if with_features:
+        rs = np.random.RandomState(seed + 1)
+        feats = np.zeros((n + 1, f), dtype=np.float32)
+        feats[:n] = rs.standard_normal((n, f)).astype(np.float32)
+        out["features"] = feats
+    return out

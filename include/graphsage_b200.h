@@ -1,0 +1,149 @@
+/*
+ * graphsage_b200.h - C-ABI of libgraphsage_b200.so (sm_100a).
+ *
+ * The reference (williamleif/GraphSAGE) has NO FFI boundary: its hot path is python
+ * classes composing TensorFlow library ops.  Each entry point below therefore names the
+ * TF op sequence (reference file:line) it replaces; the python classes that keep the
+ * reference's surface (graphsage_b200/{neigh_samplers,aggregators,models}.py) bind these
+ * through ctypes.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - Pointers are DEVICE pointers unless the name ends in _host.  Row-major.  "pitch"/"ld"
+ *     are in ELEMENTS.  The library never allocates or frees device memory and never
+ *     synchronises: every call only enqueues work on `stream` (a cudaStream_t passed as void*).
+ *   - Return value: 0 = OK, <0 = gs_status error; gs_last_error_string() (thread-local, host)
+ *     describes the last failure.  No exceptions cross the boundary.
+ *   - There is no CPU fallback: without a CUDA device every compute entry returns GS_ERR_CUDA.
+ */
+#ifndef GRAPHSAGE_B200_H_
+#define GRAPHSAGE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GS_ABI_VERSION 1
+
+typedef enum {
+  GS_OK = 0,
+  GS_ERR_INVALID_ARG = -1,
+  GS_ERR_CUDA = -2,
+  GS_ERR_UNSUPPORTED = -3
+} gs_status;
+
+typedef enum { GS_F32 = 0, GS_BF16 = 1 } gs_dtype;
+typedef enum { GS_ACT_NONE = 0, GS_ACT_RELU = 1 } gs_act;
+/* how the neighbour part and the self part are combined */
+typedef enum {
+  GS_COMBINE_ADD = 0,    /* tf.add_n([from_self, from_neighs])      aggregators.py:55-56 */
+  GS_COMBINE_CONCAT = 1  /* tf.concat([from_self, from_neighs], 1)  aggregators.py:57-58 */
+} gs_combine;
+/* arithmetic of the dense contraction */
+typedef enum {
+  GS_MATH_FP32_SIMT = 0,  /* fp32 FFMA on CUDA cores (bring-up / cross-check path)          */
+  GS_MATH_TF32X3 = 1,     /* tcgen05 kind::tf32, 3-term hi/lo split, fp32 accumulate in TMEM */
+  GS_MATH_TF32 = 2,       /* tcgen05 kind::tf32 single pass                                  */
+  GS_MATH_BF16 = 3        /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate              */
+} gs_math;
+
+int32_t gs_version(void);
+const char* gs_last_error_string(void);
+/* tuning knobs for experiments (e.g. "gather_variant" 0=ldg 1=tma-bulk); returns previous value */
+int32_t gs_set_tuning(const char* key, int32_t value);
+
+/* ---------------------------------------------------------------------------------------------
+ * UniformNeighborSampler._call           reference graphsage/neigh_samplers.py:24-29
+ *   out[i, j] = adj[ids[i], pi[j]], j < k, ONE column permutation pi per call.
+ *   pi = col_perm (device int32[>=k]) if non-null, else the on-device Philox4x32-10 forward
+ *   Fisher-Yates prefix of (seed, counter + (counter_dev ? *counter_dev : 0)) - bit-identical to
+ *   oracle/sampler.py:perm_prefix.  ids outside [0, n_rows) read the dummy row n_rows-1.
+ * --------------------------------------------------------------------------------------------- */
+int32_t gs_sample_padded(const int32_t* adj, int64_t n_rows, int32_t max_deg,
+                         const int32_t* ids, int64_t n, int32_t k,
+                         const int32_t* col_perm, uint64_t seed, uint64_t counter,
+                         const uint64_t* counter_dev, int32_t* out, void* stream);
+
+/* Per-node draws from a CSR adjacency (north_star's warp-per-node mode; no reference
+ * counterpart).  Semantics: oracle/sampler.py:sample_csr.  k <= 32. */
+int32_t gs_sample_csr(const int64_t* indptr, const int32_t* indices, int64_t n_nodes,
+                      const int32_t* ids, int64_t n, int32_t k, int32_t replace_if_short,
+                      uint64_t seed, uint64_t counter, const uint64_t* counter_dev,
+                      int32_t pad_id, int32_t* out, void* stream);
+
+/* host helper: the first k entries of pi for (seed, counter) - what the kernel computes */
+int32_t gs_perm_prefix_host(uint64_t seed, uint64_t counter, int32_t max_deg, int32_t k,
+                            int32_t* out_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * tf.nn.embedding_lookup(features, ids)   reference graphsage/models.py:299
+ *   out[i, 0:F] = feats[ids[i], 0:F].  When row bytes are 16-B multiples and pointers 16-B
+ *   aligned the copy is staged global->shared->global by the TMA bulk-copy engine.
+ * --------------------------------------------------------------------------------------------- */
+int32_t gs_gather_rows(const void* feats, int32_t dtype, int64_t n_rows, int32_t F,
+                       int64_t pitch, const int32_t* ids, int64_t n, void* out,
+                       int64_t out_pitch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused K-hop gather + fixed-fanout segmented mean:
+ *   tf.nn.embedding_lookup (models.py:299) + tf.reduce_mean(neigh_vecs, axis=1)
+ *   (aggregators.py:48), or the GCN form mean(concat([neigh, self]))  (aggregators.py:106-107),
+ *   without materialising the [n*k, F] neighbour tensor.
+ * A call processes up to GS_MAX_SEGMENTS segments (one per hop) in one launch.  For segment s,
+ * output row r = out_row0 + i (i < n):
+ *   neigh row j of i = src[neigh_ids ? neigh_ids[i*k + j] : neigh_row0 + i*k + j]
+ *   self  row   of i = src[self_ids  ? self_ids[i]        : self_row0 + i]
+ *   out_mean[r] = (sum_j neigh_j (+ self if include_self)) / (k (+1 if include_self))
+ *   out_self[r] = self row (only if out_self != NULL)
+ * src is [n_src_rows, F] with `pitch`; F columns are produced, columns F..out_pitch-1 are zeroed.
+ * --------------------------------------------------------------------------------------------- */
+#define GS_MAX_SEGMENTS 4
+typedef struct {
+  const int32_t* self_ids;   /* device, may be NULL */
+  const int32_t* neigh_ids;  /* device, may be NULL */
+  int64_t self_row0;
+  int64_t neigh_row0;
+  int64_t n;
+  int32_t k;
+  int32_t _pad;
+  int64_t out_row0;
+} gs_segment;
+
+int32_t gs_gather_mean(const void* src, int32_t dtype, int64_t n_src_rows, int32_t F, int64_t pitch,
+                       const gs_segment* segments_host, int32_t n_segments, int32_t include_self,
+                       void* out_self, void* out_mean, int64_t out_pitch, void* stream);
+
+/* segmented max over fixed fanout: out[i, c] = max_j x[i*k + j, c]   (aggregators.py:182) */
+int32_t gs_segment_max(const float* x, int64_t n, int32_t k, int32_t C, int64_t ldx,
+                       float* out, int64_t ldo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The dense contraction of an aggregator (aggregators.py:51-64, 110-116, 184-195; Dense
+ * layers.py:104-116):
+ *   part p (p < n_parts <= 2):  P_p = A_p[M, K_p] @ B_p[K_p, N_p]      (B row-major, ldb)
+ *   combine ADD   : out[:, 0:N]            = act(P_0 + P_1 + bias)      (N_0 == N_1)
+ *   combine CONCAT: out[:, 0:N_0]          = act(P_0 + bias[0:N_0]),
+ *                   out[:, N_0:N_0+N_1]    = act(P_1 + bias[N_0:])
+ *   bias may be NULL.  fp32 in/out.  `math` selects the arithmetic (gs_math).
+ *   workspace: device scratch of gs_sage_gemm_workspace_bytes(...) bytes (may be NULL if 0).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* A; int64_t lda; int32_t K;
+  const float* B; int64_t ldb; int32_t N;
+} gs_gemm_part;
+
+int64_t gs_sage_gemm_workspace_bytes(int64_t M, const gs_gemm_part* parts_host, int32_t n_parts,
+                                     int32_t math);
+int32_t gs_sage_gemm(int64_t M, const gs_gemm_part* parts_host, int32_t n_parts, int32_t combine,
+                     const float* bias, int32_t act, int32_t math, float* out, int64_t ldo,
+                     void* workspace, void* stream);
+
+/* tf.nn.l2_normalize(x, 1)   reference graphsage/models.py:368-370, supervised_models.py:85 */
+int32_t gs_l2_normalize_rows(float* x, int64_t n, int32_t C, int64_t ldx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAPHSAGE_B200_H_ */

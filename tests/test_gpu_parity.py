@@ -1,0 +1,316 @@
+"""GPU: parity of the CUDA path (through the C-ABI) against the oracle and the committed golden
+vectors.  Bit-exact for integer work; fp32 layer outputs within 1e-4 relative (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4   # north_star: "fp32 layer outputs within 1e-4 rel"
+
+
+@pytest.fixture(scope="module")
+def gs():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import graphsage_b200
+    graphsage_b200._lib.lib()        # raises if the .so is missing: no silent fallback
+    return graphsage_b200
+
+
+def dev(x, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+MATHS = ["fp32"]
+
+
+# ---------------------------------------------------------------- K1 sampler
+def test_sampler_golden_bit_exact(gs):
+    g = load_golden("sampler")
+    for ci in range(int(g["n_cases"])):
+        out = gs.ops.sample_padded(dev(g["adj%d" % ci]), dev(g["ids%d" % ci]), int(g["k%d" % ci]),
+                                   int(g["seed%d" % ci]), int(g["counter%d" % ci]))
+        assert out.dtype == torch.int32
+        np.testing.assert_array_equal(out.cpu().numpy(), g["out%d" % ci])
+
+
+def test_sampler_class_counter_and_swap(gs):
+    rs = np.random.RandomState(3)
+    n, md = 1000, 128
+    adj = rs.randint(0, n, size=(n + 1, md)).astype(np.int32)
+    adj[n] = n
+    ids = rs.randint(0, n + 1, size=777).astype(np.int32)
+    s = gs.UniformNeighborSampler(dev(adj), seed=11)
+    a = s((dev(ids), 10)).cpu().numpy()
+    b = s((dev(ids), 25)).cpu().numpy()          # second call -> counter 1 -> fresh permutation
+    np.testing.assert_array_equal(a, oracle.sample_padded(adj, ids, 10, 11, 0))
+    np.testing.assert_array_equal(b, oracle.sample_padded(adj, ids, 25, 11, 1))
+    # same column set for every row of a call (neigh_samplers.py:27), columns distinct
+    pi = oracle.perm_prefix(11, 1, md, 25)
+    assert len(set(pi.tolist())) == 25
+    adj2 = np.roll(adj, 1, axis=1).copy()
+    s.set_adj(dev(adj2))
+    c = s((dev(ids), 25)).cpu().numpy()
+    np.testing.assert_array_equal(c, oracle.sample_padded(adj2, ids, 25, 11, 2))
+    # full-width sample, explicit permutation, device-side counter, empty batch
+    full = gs.ops.sample_padded(dev(adj), dev(ids), md, 5, 9).cpu().numpy()
+    np.testing.assert_array_equal(full, oracle.sample_padded(adj, ids, md, 5, 9))
+    perm = rs.permutation(md).astype(np.int32)
+    e = gs.ops.sample_padded(dev(adj), dev(ids), 7, 0, 0, col_perm=dev(perm)).cpu().numpy()
+    np.testing.assert_array_equal(e, adj[ids][:, perm[:7]])
+    cdev = torch.tensor([1 << 35], dtype=torch.int64).cuda()
+    f = gs.ops.sample_padded(dev(adj), dev(ids), 10, 11, 4, counter_dev=cdev).cpu().numpy()
+    np.testing.assert_array_equal(f, oracle.sample_padded(adj, ids, 10, 11, 4 + (1 << 35)))
+    assert gs.ops.sample_padded(dev(adj), dev(ids[:0]), 10, 1, 1).shape == (0, 10)
+    with pytest.raises(RuntimeError, match="num_samples"):
+        gs.ops.sample_padded(dev(adj), dev(ids), md + 1, 1, 1)
+    oob = np.array([-5, n + 7], dtype=np.int32)             # out-of-range ids read the dummy row
+    assert (gs.ops.sample_padded(dev(adj), dev(oob), 4, 1, 1).cpu().numpy() == n).all()
+
+
+def test_sample_csr_bit_exact(gs):
+    rs = np.random.RandomState(5)
+    n = 5000
+    deg = rs.randint(0, 60, size=n)
+    deg[:4] = [0, 1, 25, 26]
+    indptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    indices = rs.randint(0, n, size=int(indptr[-1])).astype(np.int32)
+    ids = rs.randint(0, n, size=3333).astype(np.int32)
+    ids[:4] = [0, 1, 2, 3]
+    for k in (1, 10, 25, 32):
+        for rep in (True, False):
+            out = gs.ops.sample_csr(dev(indptr), dev(indices), dev(ids), k, 77, 5, rep, pad_id=n).cpu().numpy()
+            np.testing.assert_array_equal(out, oracle.sample_csr(indptr, indices, ids, k, 77, 5, rep, pad_id=n))
+    with pytest.raises(RuntimeError, match="not supported"):
+        gs.ops.sample_csr(dev(indptr), dev(indices), dev(ids), 33, 1, 1)
+
+
+# ---------------------------------------------------------------- K2 gather
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("F", [602, 50, 256, 7])
+def test_gather_rows_exact(gs, variant, F):
+    rs = np.random.RandomState(F)
+    n = 4097
+    feats = rs.randn(n + 1, F).astype(np.float32)
+    ids = rs.randint(0, n + 1, size=10001).astype(np.int32)
+    gs._lib.set_tuning("gather_variant", variant)
+    try:
+        P = gs.ops.pad_cols(F)
+        table = torch.zeros((n + 1, P), dtype=torch.float32, device="cuda")
+        table[:, :F] = dev(feats)
+        out = gs.ops.gather_rows(table[:, :F], dev(ids))          # pitched table view (pitch 608 for F=602)
+        np.testing.assert_array_equal(out.cpu().numpy(), feats[ids])
+        out2 = gs.ops.gather_rows(dev(feats), dev(ids))           # dense pitch == F
+        np.testing.assert_array_equal(out2.cpu().numpy(), feats[ids])
+        outp = torch.empty((len(ids), P), dtype=torch.float32, device="cuda")
+        gs.ops.gather_rows(table, dev(ids), out=outp)             # whole padded rows: the TMA bulk path
+        np.testing.assert_array_equal(outp[:, :F].cpu().numpy(), feats[ids])
+        bf = table.to(torch.bfloat16)
+        ob = gs.ops.gather_rows(bf, dev(ids))
+        assert torch.equal(ob, bf[dev(ids).long()])
+    finally:
+        gs._lib.set_tuning("gather_variant", 1)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_gather_mean_matches_numpy(gs, variant):
+    rs = np.random.RandomState(9)
+    n_src, F = 3000, 602
+    P = gs.ops.pad_cols(F)
+    feats = rs.randn(n_src, F).astype(np.float32)
+    table = torch.full((n_src, P), 7.0, dtype=torch.float32, device="cuda")   # poison the pad columns
+    table[:, :F] = dev(feats)
+    src = table[:, :F]
+    n0, k0, n1, k1 = 64, 10, 640, 25
+    s0 = rs.randint(0, n_src, size=n0).astype(np.int32)
+    s1 = rs.randint(0, n_src, size=n0 * k0).astype(np.int32)
+    s2 = rs.randint(0, n_src, size=n1 * k1).astype(np.int32)
+    gs._lib.set_tuning("gather_variant", variant)
+    try:
+        segs = [gs.ops.Seg(n0, k0, self_ids=dev(s0), neigh_ids=dev(s1), out_row0=0),
+                gs.ops.Seg(n1, k1, self_ids=dev(s1), neigh_ids=dev(s2), out_row0=n0)]
+        for include_self in (False, True):
+            xs, xm = gs.ops.gather_mean(src, segs, include_self=include_self)
+            xs, xm = xs.cpu().numpy(), xm.cpu().numpy()
+            assert xs.shape == (n0 + n1, P) and (xs[:, F:] == 0).all() and (xm[:, F:] == 0).all()
+            np.testing.assert_array_equal(xs[:, :F], feats[np.concatenate([s0, s1])])
+            nb0 = feats[s1].reshape(n0, k0, F)
+            nb1 = feats[s2].reshape(n1, k1, F)
+            if include_self:
+                ref = np.concatenate([(nb0.sum(1) + feats[s0]) / (k0 + 1), (nb1.sum(1) + feats[s1]) / (k1 + 1)])
+            else:
+                ref = np.concatenate([nb0.mean(1), nb1.mean(1)])
+            assert rel_err(xm[:, :F], ref) < 1e-5
+        # dense (id-free) form: rows addressed by ranges
+        H = rs.randn(n0 + n0 * k0, 256).astype(np.float32)
+        _, m = gs.ops.gather_mean(dev(H), [gs.ops.Seg(n0, k0, self_row0=0, neigh_row0=n0)], want_self=False)
+        assert rel_err(m.cpu().numpy()[:, :256], H[n0:].reshape(n0, k0, 256).mean(1)) < 1e-5
+    finally:
+        gs._lib.set_tuning("gather_variant", 1)
+
+
+def test_gather_mean_odd_width_scalar_path(gs):
+    rs = np.random.RandomState(2)
+    x = rs.randn(500, 7).astype(np.float32)                  # pitch 7: no 16-B alignment -> scalar kernel
+    ids = rs.randint(0, 500, size=30 * 4).astype(np.int32)
+    sid = rs.randint(0, 500, size=30).astype(np.int32)
+    xs, xm = gs.ops.gather_mean(dev(x), [gs.ops.Seg(30, 4, self_ids=dev(sid), neigh_ids=dev(ids))])
+    np.testing.assert_array_equal(xs.cpu().numpy()[:, :7], x[sid])
+    assert rel_err(xm.cpu().numpy()[:, :7], x[ids].reshape(30, 4, 7).mean(1)) < 1e-6
+
+
+# ---------------------------------------------------------------- aggregators (golden = reference code under shim)
+def _inject(agg, **weights):
+    for k, v in weights.items():
+        assert tuple(agg.vars[k].shape) == tuple(v.shape), (k, agg.vars[k].shape, v.shape)
+        agg.vars[k] = dev(v)
+
+
+@pytest.mark.parametrize("math", MATHS)
+def test_aggregators_golden(gs, math):
+    g = load_golden("aggregators")
+    gs.set_default_math(math)
+    s, n = dev(g["self"]), dev(g["neigh"])
+    for c in (0, 1):
+        agg = gs.MeanAggregator(50, 16, concat=bool(c))
+        assert set(agg.vars) == {"neigh_weights", "self_weights"}
+        _inject(agg, neigh_weights=g["mean_c%d_nw" % c], self_weights=g["mean_c%d_sw" % c])
+        y = agg((s, n))
+        assert tuple(y.shape) == (37, 16 * (1 + c))
+        assert rel_err(y.cpu().numpy(), g["mean_c%d_out" % c]) < TOL
+        agg = gs.MaxPoolingAggregator(50, 16, concat=bool(c))
+        assert agg.hidden_dim == 512 and set(agg.mlp_layers[0].vars) == {"weights", "bias"}
+        _inject(agg, neigh_weights=g["maxpool_c%d_nw" % c], self_weights=g["maxpool_c%d_sw" % c])
+        _inject(agg.mlp_layers[0], weights=g["maxpool_c%d_mw" % c], bias=g["maxpool_c%d_mb" % c])
+        y = agg((s, n))
+        assert rel_err(y.cpu().numpy(), g["maxpool_c%d_out" % c]) < TOL
+    agg = gs.GCNAggregator(50, 16)
+    assert set(agg.vars) == {"weights"}
+    _inject(agg, weights=g["gcn_w"])
+    assert rel_err(agg((s, n)).cpu().numpy(), g["gcn_out"]) < TOL
+    agg = gs.MeanAggregator(50, 16, neigh_input_dim=24, act=lambda x: x, concat=True)
+    _inject(agg, neigh_weights=g["mean_id_nw"], self_weights=g["mean_id_sw"])
+    assert rel_err(agg((s, dev(g["neigh2"]))).cpu().numpy(), g["mean_id_out"]) < TOL
+    gs.set_default_math("fp32")
+
+
+def test_glorot_range_and_bias(gs):
+    w = gs.inits.glorot([602, 128]).cpu().numpy()
+    r = oracle.glorot_range((602, 128))
+    assert w.dtype == np.float32 and np.abs(w).max() <= r and np.abs(w).max() > 0.99 * r and abs(w.mean()) < 1e-3
+    agg = gs.MeanAggregator(8, 4, bias=True, concat=True)      # reference crashes here (appendix A); we support it
+    agg.vars["bias"] = dev(np.arange(8, dtype=np.float32))
+    x, nb = torch.zeros(3, 8).cuda(), torch.zeros(3, 2, 8).cuda()
+    np.testing.assert_allclose(agg((x, nb)).cpu().numpy(), np.tile(np.arange(8, dtype=np.float32), (3, 1)))
+
+
+# ---------------------------------------------------------------- K-hop recursion (golden)
+_KEYMAP = {"neigh_weights": "neigh_weights", "self_weights": "self_weights", "weights": "weights"}
+
+
+def _build_model(gs, g, model, seed=123, counter=40):
+    kind = {"mean": "mean", "mean3": "mean", "gcn": "gcn", "maxpool": "maxpool"}[model]
+    fan = [int(x) for x in g[model + "_fanout"]]
+    dims = [int(x) for x in g[model + "_dims"]]
+    sampler = gs.UniformNeighborSampler(dev(g["adj"]), seed=seed)
+    sampler.counter = counter
+    infos = [gs.SAGEInfo("node", sampler, fan[i], dims[i + 1]) for i in range(len(fan))]
+    m = gs.SampleAndAggregate({"batch_size": len(g["seeds"]), "dropout": 0.}, dev(g["feats"]), dev(g["adj"]), None,
+                              infos, concat=bool(g[model + "_concat"]), aggregator_type=kind)
+    return m, infos, fan, dims
+
+
+@pytest.mark.parametrize("math", MATHS)
+@pytest.mark.parametrize("model", ["mean", "gcn", "maxpool", "mean3"])
+def test_khop_golden(gs, model, math):
+    g = load_golden("khop")
+    gs.set_default_math(math)
+    m, infos, fan, dims = _build_model(gs, g, model)
+    samples, support = m.sample(dev(g["seeds"]), infos)
+    assert support == [int(x) for x in g[model + "_support"]]
+    for h, s in enumerate(samples):
+        np.testing.assert_array_equal(s.cpu().numpy(), g["%s_samples%d" % (model, h)])       # bit-exact indices
+    out, aggs = m.aggregate(samples, [m.features], dims, fan, support, concat=bool(g[model + "_concat"]))
+    # inject the reference's weights, then re-run with the same aggregators (models.py:316-317)
+    for li, a in enumerate(aggs):
+        for key in list(a.vars):
+            _inject(a, **{key: g["%s_L%d_%s" % (model, li, key)]})
+        if hasattr(a, "mlp_layers"):
+            _inject(a.mlp_layers[0], weights=g["%s_L%d_mlp_weights" % (model, li)],
+                    bias=g["%s_L%d_mlp_bias" % (model, li)])
+    out, _ = m.aggregate(samples, [m.features], dims, fan, support, aggregators=aggs,
+                         concat=bool(g[model + "_concat"]))
+    assert rel_err(out.cpu().numpy(), g[model + "_out"]) < TOL
+    out_l2 = gs.ops.l2_normalize_rows_(out.clone())
+    assert rel_err(out_l2.cpu().numpy(), g[model + "_out_l2"]) < TOL
+    # the literal (materialised) recursion gives the same answer as the gather-fused one
+    lit = m._aggregate_materialised(samples, m.features, dims, fan, support, len(g["seeds"]), aggs,
+                                    bool(g[model + "_concat"]))
+    assert rel_err(lit.cpu().numpy(), g[model + "_out"]) < TOL
+    gs.set_default_math("fp32")
+
+
+# ---------------------------------------------------------------- full-size Reddit shape (BASELINE configs[1])
+@pytest.fixture(scope="module")
+def reddit(gs):
+    from graphsage_b200.synthetic import reddit_like
+    g = reddit_like(n=232965, f=602, max_degree=128, seed=123)
+    P = gs.ops.pad_cols(602)
+    table = torch.zeros((g["n"] + 1, P), dtype=torch.float32, device="cuda")
+    table[:, :602] = torch.from_numpy(g["features"]).cuda()
+    g["table"] = table
+    g["adj_dev"] = torch.from_numpy(g["adj"]).cuda()
+    return g
+
+
+@pytest.mark.parametrize("math", MATHS)
+@pytest.mark.parametrize("kind,concat,dim", [("mean", True, 128), ("gcn", False, 256)])
+def test_full_size_forward_vs_oracle(gs, reddit, kind, concat, dim, math):
+    gs.set_default_math(math)
+    g = reddit
+    rs = np.random.RandomState(1)
+    B = 512
+    seeds = rs.randint(0, g["n"], size=B).astype(np.int32)
+    sampler = gs.UniformNeighborSampler(g["adj_dev"], seed=123)
+    infos = [gs.SAGEInfo("node", sampler, 25, dim), gs.SAGEInfo("node", sampler, 10, dim)]
+    m = gs.SampleAndAggregate({"batch_size": B, "dropout": 0.}, g["table"][:, :602], g["adj_dev"], None, infos,
+                              concat=concat, aggregator_type=kind)
+    out = m.forward(torch.from_numpy(seeds), normalize=True)
+    assert tuple(out.shape) == (B, 256)
+    aggs = []
+    for a in m.aggregators:
+        d = {"type": kind}
+        d.update({k: v.cpu().numpy() for k, v in a.vars.items()})
+        aggs.append(d)
+    ref = oracle.forward_2hop(g["adj"], g["features"], seeds, [25, 10], aggs, concat, 123, 0, normalize=True)
+    assert rel_err(out.cpu().numpy(), ref) < TOL
+    # size-independent properties: unit rows; sampled ids are members of the adjacency rows
+    assert np.allclose(np.linalg.norm(out.cpu().numpy(), axis=1), 1.0, atol=1e-5)
+    sampler.counter = 0
+    samples, support = m.sample(torch.from_numpy(seeds).cuda(), infos)
+    assert [s.numel() for s in samples] == [512, 5120, 128000] and support == [1, 10, 250]
+    s1 = samples[1].cpu().numpy().reshape(B, 10)
+    s2 = samples[2].cpu().numpy().reshape(B * 10, 25)
+    for i in range(0, B, 17):
+        assert set(s1[i].tolist()) <= set(g["adj"][seeds[i]].tolist())
+    for i in range(0, B * 10, 311):
+        assert set(s2[i].tolist()) <= set(g["adj"][s1.reshape(-1)[i]].tolist())
+    gs.set_default_math("fp32")
+
+
+def test_full_size_gather_checksum(gs, reddit):
+    g = reddit
+    rs = np.random.RandomState(4)
+    ids = rs.randint(0, g["n"] + 1, size=133632).astype(np.int32)     # one batch's 512*(1+10+250) rows
+    out = gs.ops.gather_rows(g["table"], dev(ids))
+    ref = g["table"][dev(ids).long()]
+    assert torch.equal(out, ref)
+    # gathering is linear in the table: gather(a*T) == a*gather(T) exactly for a power of two
+    out2 = gs.ops.gather_rows(g["table"] * 2.0, dev(ids))
+    assert torch.equal(out2, out * 2.0)

@@ -130,3 +130,16 @@ def test_sample_csr_properties():
     # different counters give different draws, same counter reproduces
     np.testing.assert_array_equal(out, oracle.sample_csr(indptr, indices, ids, k, 7, 3, True, pad_id=-1))
     assert (out != oracle.sample_csr(indptr, indices, ids, k, 7, 4, True, pad_id=-1)).any()
+
+
+def test_torch_cpu_baseline_matches_numpy_oracle():
+    import torch
+    from oracle import torch_ref
+    g = load_golden("khop")
+    for model, kind in (("mean", "mean"), ("gcn", "gcn"), ("maxpool", "maxpool")):
+        fan = [int(x) for x in g[model + "_fanout"]]
+        aggs = [{k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in a.items() if k != "type"}
+                for a in _aggs(g, model, len(fan))]
+        out = torch_ref.forward(torch.from_numpy(g["adj"]), torch.from_numpy(g["feats"]), torch.from_numpy(g["seeds"]),
+                                fan, aggs, bool(g[model + "_concat"]), kind, 123, 40, normalize=True)
+        assert rel_err(out.numpy(), g[model + "_out_l2"]) < 1e-5
