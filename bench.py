@@ -97,10 +97,22 @@ def make_weights(kind, rs):
 def cpu_reference_rate(g, kind, weights, n_batches, warm, seed_rs):
     """The reference op sequence on the host cores (oracle/torch_ref.py); seeds/s over n_batches."""
     from oracle import torch_ref
-    torch.set_num_threads(len(os.sched_getaffinity(0)))
     adj_t, feats_t = torch.from_numpy(g["adj"]), torch.from_numpy(g["features"])
     aggs = [{k: torch.from_numpy(v) for k, v in w.items()} for w in weights]
     concat = kind == "mean"
+    # use the thread count that is fastest on this host (all cores is often slower for the gather)
+    ncpu = len(os.sched_getaffinity(0))
+    best = (None, 1e30)
+    probe_seeds = torch.from_numpy(np.random.RandomState(5).randint(0, N_NODES, size=BATCH).astype(np.int32))
+    for nt in sorted({min(ncpu, t) for t in (8, 16, 32, 64, ncpu)}):
+        torch.set_num_threads(nt)
+        torch_ref.forward(adj_t, feats_t, probe_seeds, FANOUT, aggs, concat, kind, 123, 0, normalize=True)
+        t0 = time.perf_counter()
+        torch_ref.forward(adj_t, feats_t, probe_seeds, FANOUT, aggs, concat, kind, 123, 0, normalize=True)
+        dt = time.perf_counter() - t0
+        if dt < best[1]:
+            best = (nt, dt)
+    torch.set_num_threads(best[0])
     times = []
     for i in range(warm + n_batches):
         seeds = torch.from_numpy(seed_rs.randint(0, N_NODES, size=BATCH).astype(np.int32))
@@ -193,45 +205,48 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident timing ("value")
+    probe_name = "gather_mean/%d" % (BATCH * 11)
+    runner = model.graphed(BATCH, normalize=True, probe=probe_name)     # CUDA-graph replay of forward()
+
+    # ---- device-resident timing ("value"): inputs already in HBM
     for i in range(args.warmup):
-        model.forward(seeds_dev[i])
+        runner(seeds_dev[i])
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
-    ops.PROBE = {}
-    launches0 = ops.LAUNCHES
+    probe_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        out = model.forward(seeds_dev[args.warmup + i])
+        out = runner(seeds_dev[args.warmup + i], probe_events=probe_events[i])
     e1.record()
     barrier()
-    launches = ops.LAUNCHES - launches0
+    launches = runner.launches_per_replay * args.steps
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    probe, ops.PROBE = ops.PROBE, None
+    probe = {probe_name: probe_events}
     clk = clocks.summary()
     value = world * BATCH * args.steps / (ms_total * 1e-3)
 
     # ---- end-to-end through the public API with host buffers (H2D of ids, D2H of the result, every step)
     for i in range(min(args.warmup, 5)):
-        model.forward(seeds_host[i].to(dev, non_blocking=True))
+        runner(seeds_host[i])
     barrier()
     e0.record()
     for i in range(args.steps):
-        ids = seeds_host[args.warmup + i].to(dev, non_blocking=True)
-        out = model.forward(ids)
-        out_host[i].copy_(out, non_blocking=True)
+        out = runner(seeds_host[args.warmup + i])          # pinned host ids -> device (async copy on the stream)
+        out_host[i].copy_(out, non_blocking=True)          # result -> pinned host
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = world * BATCH * args.steps / (ms_e2e * 1e-3)
+    check = float(out_host[-1].abs().sum())                # the host really received the last result
+    assert np.isfinite(check) and check > 0
 
     if rank != 0:
         return
     # ---- roofline of the dominant kernel: the layer-0 fused gather+mean
     peak, peak_src = peaks()
-    key = "gather_mean/%d" % (BATCH * 11)
+    key = probe_name
     durs = [a.elapsed_time(b) for a, b in probe.get(key, [])]
     roof = None
     if durs:

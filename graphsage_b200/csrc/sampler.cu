@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256) sample_padded_kernel(const int32_t* __res
       u32x4 r{0, 0, 0, 0};
       for (int i = 0; i < k; ++i) {
         if ((i & 3) == 0) {
-          u32x4 c{(uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)(i >> 2), kStreamPadded};
+          u32x4 c{(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, kStreamPadded + (uint32_t)(i >> 2)};  // oracle/sampler.py:_draws
           r = philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
         }
         int j = i + (int)mulhi32(pick(r, i & 3), (uint32_t)(max_deg - i));

@@ -139,6 +139,10 @@ class SampleAndAggregate(object):
         return hidden[0]
 
     # ------------------------------------------------------------------ convenience: the whole path
+    def graphed(self, batch_size, normalize=True, probe=None):
+        """CUDA-graph runner of forward() for a fixed batch size (see GraphedForward)."""
+        return GraphedForward(self, batch_size, normalize, probe)
+
     def forward(self, batch, normalize=True):
         """sample -> aggregate -> l2_normalize (reference models.py:347-350, 368) for one id batch."""
         batch = batch.to(device=self.device, dtype=torch.int32).reshape(-1)
@@ -151,3 +155,89 @@ class SampleAndAggregate(object):
         if normalize:
             out = ops.l2_normalize_rows_(out.contiguous())
         return out
+
+
+class GraphedForward(object):
+    """SampleAndAggregate.forward for a fixed batch size captured into CUDA graph(s): one replay =
+    one batch through sample -> gather -> aggregate (-> l2_normalize) with no per-kernel host work.
+
+    The samplers' RNG call counter lives on the device (`self.counter`) and is advanced by the graph
+    itself, so replay r draws exactly what the r-th eager forward would draw (counter0 + n_calls*r + j).
+    `probe` (an ops probe name such as "gather_mean/5632") isolates that launch in its own graph so
+    bench.py can bracket it with CUDA events inside the timed region.
+    """
+
+    def __init__(self, model, batch_size, normalize=True, probe=None):
+        self.model, self.batch_size, self.normalize = model, int(batch_size), normalize
+        dev = model.device
+        self.ids = torch.zeros(self.batch_size, dtype=torch.int32, device=dev)
+        self.counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        samplers = []
+        for info in model.layer_infos:
+            if all(info.neigh_sampler is not s for s in samplers):
+                samplers.append(info.neigh_sampler)
+        self.samplers = samplers
+        self.base_counters = [s.counter for s in samplers]
+        self.n_calls = len(model.layer_infos)
+        self.graphs, self.probe_index = [], None
+        self.stream = torch.cuda.Stream(device=dev)
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self.stream):
+            for _ in range(2):                                 # warm-up: lazy inits, aggregator creation
+                model.forward(self.ids, normalize)
+            self._reset_python_counters()
+            for s in samplers:
+                s.counter_dev = self.counter
+            pool = torch.cuda.graph_pool_handle()
+            state = {"g": torch.cuda.CUDAGraph()}
+            state["g"].capture_begin(pool=pool)
+
+            def hook(name, phase):
+                if probe is None or name != probe:
+                    return
+                state["g"].capture_end()
+                self.graphs.append(state["g"])
+                if phase == "pre":
+                    self.probe_index = len(self.graphs)
+                state["g"] = torch.cuda.CUDAGraph()
+                state["g"].capture_begin(pool=pool)
+
+            ops.STAGE_HOOK = hook
+            try:
+                launches0 = ops.LAUNCHES
+                self.out = model.forward(self.ids, normalize)
+                self.counter.add_(self.n_calls)
+                self.launches_per_replay = ops.LAUNCHES - launches0
+            finally:
+                ops.STAGE_HOOK = None
+                state["g"].capture_end()
+                self.graphs.append(state["g"])
+            self._reset_python_counters()
+        torch.cuda.current_stream(dev).wait_stream(self.stream)
+        self.replays = 0
+
+    def _reset_python_counters(self):
+        for s, c in zip(self.samplers, self.base_counters):
+            s.counter = c
+
+    def reset(self, replays=0):
+        """Next replay behaves like eager forward number `replays` since construction."""
+        self.counter.fill_(self.n_calls * replays)
+        self.replays = replays
+
+    def __call__(self, ids=None, probe_events=None):
+        if ids is not None:
+            self.ids.copy_(ids.reshape(-1), non_blocking=True)
+        for gi, g in enumerate(self.graphs):
+            if probe_events is not None and gi == self.probe_index:
+                probe_events[0].record()
+                g.replay()
+                probe_events[1].record()
+            else:
+                g.replay()
+        self.replays += 1
+        return self.out
+
+    def close(self):
+        for s in self.samplers:
+            s.counter_dev = None

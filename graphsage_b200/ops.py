@@ -11,15 +11,27 @@ _U64 = 2**64 - 1
 # optional per-kernel timing (bench.py): name -> list of (start_event, end_event) on the current stream
 PROBE = None
 LAUNCHES = 0          # kernels of ours launched through this module (bench.py reports it as gpu_launches)
+STAGE_HOOK = None     # callable(name, "pre"|"post") around probe-able launches (models.GraphedForward splits graphs here)
 
 
 def _probe(name):
+    if STAGE_HOOK is not None:
+        STAGE_HOOK(name, "pre")
     if PROBE is None:
-        return None
+        return _PostHook(name) if STAGE_HOOK is not None else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     PROBE.setdefault(name, []).append((e0, e1))
     e0.record()
     return e1
+
+
+class _PostHook(object):
+    def __init__(self, name):
+        self.name = name
+
+    def record(self):
+        if STAGE_HOOK is not None:
+            STAGE_HOOK(self.name, "post")
 
 
 def _launched(n=1, ev=None):

@@ -314,3 +314,26 @@ def test_full_size_gather_checksum(gs, reddit):
     # gathering is linear in the table: gather(a*T) == a*gather(T) exactly for a power of two
     out2 = gs.ops.gather_rows(g["table"] * 2.0, dev(ids))
     assert torch.equal(out2, out * 2.0)
+
+
+def test_graphed_forward_matches_eager_and_oracle(gs):
+    g = load_golden("khop")
+    m, infos, fan, dims = _build_model(gs, g, "mean", counter=40)
+    B = len(g["seeds"])
+    seeds = dev(g["seeds"])
+    eager0 = m.forward(seeds, normalize=True).clone()          # counters 40, 41
+    eager1 = m.forward(seeds, normalize=True).clone()          # counters 42, 43
+    infos[0].neigh_sampler.counter = 40
+    runner = m.graphed(B, normalize=True, probe="gather_mean/%d" % (B * (1 + fan[1])))
+    assert len(runner.graphs) == 3 and runner.probe_index == 1
+    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    r0 = runner(seeds, probe_events=ev).clone()
+    r1 = runner(seeds).clone()
+    torch.cuda.synchronize()
+    assert ev[0].elapsed_time(ev[1]) > 0
+    assert torch.equal(r0, eager0) and torch.equal(r1, eager1)
+    runner.reset(0)
+    assert torch.equal(runner(seeds), eager0)
+    # replay from pinned host ids
+    assert torch.equal(runner(torch.from_numpy(g["seeds"]).pin_memory()), eager1)
+    runner.close()

@@ -26,6 +26,7 @@ def timeit(fn, nit=NIT, warm=3):
         fn(i)
     torch.cuda.synchronize()
     evs = []
+    torch.cuda._sleep(4000000)   # keep the GPU busy (~2 ms) while the host enqueues: events then see pure device time
     for i in range(nit):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
