@@ -1,11 +1,477 @@
-// tcgen05 path of gs_sage_gemm - placeholder until the UMMA kernel lands (next milestone).
+// tcgen05 path of gs_sage_gemm: the neigh_weights / self_weights contraction of the aggregators
+// (reference graphsage/aggregators.py:51-64, 110-116, 184-195; Dense graphsage/layers.py:104-116)
+// on the 5th-generation tensor cores, fp32 in / fp32 out.
+//
+//   GS_MATH_TF32X3 : A = A_hi + A_lo, B = B_hi + B_lo (each exactly representable in tf32);
+//                    D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi, fp32 accumulate in TMEM  -> fp32-grade result
+//   GS_MATH_TF32   : one kind::tf32 pass (operands masked to tf32)
+//   GS_MATH_BF16   : one kind::f16 pass, operands rounded to bf16
+//
+// Structure (one CTA = one 128 x 128 output tile, 320 threads):
+//   warps 0-7  A producers: ld.global (coalesced 128-bit, next K-block prefetched in registers) -> split /
+//              convert -> st.shared in the UMMA K-major SWIZZLE_128B layout -> fence.proxy.async -> mbarrier.
+//              The same warps run the epilogue (tcgen05.ld from TMEM, bias / ReLU, st.global).
+//   warp 8     MMA issuer: one elected thread issues tcgen05.mma (SS operands), tcgen05.commit frees stages.
+//   warp 9     B loader: cp.async.bulk of pre-swizzled weight tile images (built per call by
+//              pack_b_kernel into the caller's workspace) with mbarrier complete_tx.
+// A goes through registers on purpose: the hi/lo split (and the bf16 rounding) is arithmetic on the
+// operand, and the same producer slot later takes a row-id indirection (gather-A) for the max-pool MLP.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace gs {
-int64_t sage_gemm_tc_workspace(int64_t, const gs_gemm_part*, int32_t, int32_t) { return 0; }
-int32_t sage_gemm_tc(int64_t, const gs_gemm_part*, int32_t, int32_t, const float*, int32_t, int32_t math, float*, int64_t,
-                     void*, cudaStream_t) {
-  set_error("gs_sage_gemm: math mode %d (tcgen05) not built yet", math);
-  return GS_ERR_UNSUPPORTED;
+
+constexpr int TC_BM = 128;       // UMMA M (cta_group::1)
+constexpr int TC_BN = 128;       // UMMA N
+constexpr int TC_TILE_BYTES = TC_BM * 128;   // one operand tile image: 128 rows x 128 B (one SW128 atom wide)
+constexpr int TC_PRODUCER_WARPS = 8;
+constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 2) * 32;
+
+struct TcPart {
+  const float* A;
+  int64_t lda;
+  int32_t K;
+  int32_t N;
+  int32_t kblocks;     // ceil(K / BK)
+  int32_t ntiles;      // ceil(N / 128)
+  int64_t img_off;     // byte offset of this part's packed B images in the workspace
+  const float* B;
+  int64_t ldb;
+};
+
+struct TcParams {
+  TcPart p[2];
+  int32_t n_parts;
+  int32_t combine;
+  int64_t M;
+  const float* bias;
+  int32_t act;
+  float* out;
+  int64_t ldo;
+  int32_t tiles_n0;    // number of N tiles of part 0 (CONCAT tile -> part mapping)
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers (tcgen05 / TMEM)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
 }
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+template <bool kBf16>
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kBf16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane base + t)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
+//   [0,14) start address >> 4, [16,30) LBO >> 4 (= 1, unused for swizzled K-major),
+//   [32,46) SBO >> 4 (8 rows x 128 B = 1024 B -> 64), [46,48) version = 1, [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// cute::UMMA::InstrDescriptor: [4,6) c_format (1 = F32), [7,10) a_format, [10,13) b_format
+// (F16 = 0, BF16 = 1, TF32 = 2), [15] a_major (0 = K), [16] b_major (0 = K), [17,23) N >> 3, [24,29) M >> 4
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint32_t N) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t tf32_mask(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
+
+// byte offset of 16-byte chunk c (0..7) of row r (0..127) inside a SW128 K-major tile image
+__host__ __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
+  return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
+}
+
+// ---------------------------------------------------------------------------------------------
+// B packing: weights [K, N] row-major fp32 -> per (n tile, k block) tile images of W^T
+// (N rows x BK k-elements, K-major, SW128), hi (+ lo) or bf16.  Tiny (<= a few MB), runs per call.
+// MODE: 0 = tf32x3 (hi, lo images), 1 = tf32 (hi only), 2 = bf16
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) pack_b_kernel(TcParams prm, unsigned char* __restrict__ ws) {
+  constexpr int BK = MODE == 2 ? 64 : 32;
+  constexpr int EPC = MODE == 2 ? 8 : 4;        // elements per 16-byte chunk
+  constexpr int NIMG = MODE == 0 ? 2 : 1;
+  int unit = blockIdx.x;                        // (part, ntile, kblock) flattened
+  int pi = 0;
+  if (prm.n_parts == 2 && unit >= prm.p[0].ntiles * prm.p[0].kblocks) {
+    unit -= prm.p[0].ntiles * prm.p[0].kblocks;
+    pi = 1;
+  }
+  const TcPart& P = prm.p[pi];
+  const int nt = unit / P.kblocks, kb = unit % P.kblocks;
+  unsigned char* img = ws + P.img_off + ((int64_t)(nt * P.kblocks + kb) * NIMG) * TC_TILE_BYTES;
+  for (int q = threadIdx.x; q < 128 * 8; q += blockDim.x) {
+    const int c = q >> 7, n = q & 127;           // n fastest: coalesced reads along N
+    const int gn = nt * TC_BN + n;
+    const int k0 = kb * BK + c * EPC;
+    float w[EPC];
+#pragma unroll
+    for (int e = 0; e < EPC; ++e) w[e] = (gn < P.N && k0 + e < P.K) ? P.B[(int64_t)(k0 + e) * P.ldb + gn] : 0.f;
+    const uint32_t off = sw128_off(n, c);
+    if constexpr (MODE == 2) {
+      __nv_bfloat162 h[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(w[2 * e], w[2 * e + 1]);
+      *reinterpret_cast<uint4*>(img + off) = *reinterpret_cast<uint4*>(h);
+    } else {
+      uint4 hi;
+      hi.x = tf32_mask(w[0]); hi.y = tf32_mask(w[1]); hi.z = tf32_mask(w[2]); hi.w = tf32_mask(w[3]);
+      *reinterpret_cast<uint4*>(img + off) = hi;
+      if constexpr (MODE == 0) {
+        uint4 lo;
+        lo.x = tf32_mask(w[0] - __uint_as_float(hi.x)); lo.y = tf32_mask(w[1] - __uint_as_float(hi.y));
+        lo.z = tf32_mask(w[2] - __uint_as_float(hi.z)); lo.w = tf32_mask(w[3] - __uint_as_float(hi.w));
+        *reinterpret_cast<uint4*>(img + TC_TILE_BYTES + off) = lo;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+struct TcCfg {
+  static constexpr int BK = MODE == 2 ? 64 : 32;             // K elements per block (128 B of operand row)
+  static constexpr int UK = MODE == 2 ? 16 : 8;              // UMMA K per instruction (32 B)
+  static constexpr int NIMG = MODE == 0 ? 2 : 1;             // hi (+ lo)
+  static constexpr int STAGE_BYTES = 2 * NIMG * TC_TILE_BYTES;   // A images then B images
+  static constexpr int STAGES = MODE == 0 ? 3 : 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + slack for 1024-B alignment
+};
+
+template <int MODE>
+__device__ __forceinline__ void load_a_chunk(const TcPart& P, int64_t M, int64_t grow, int gcol, bool vec, float (&v)[8]) {
+  constexpr int EPC = MODE == 2 ? 8 : 4;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = 0.f;
+  if (grow >= M) return;
+  const float* src = P.A + grow * P.lda + gcol;
+  if (vec && gcol + EPC <= P.K) {
+    float4 a = ldg_nc_f4(reinterpret_cast<const float4*>(src));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    if constexpr (EPC == 8) {
+      float4 b = ldg_nc_f4(reinterpret_cast<const float4*>(src) + 1);
+      v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < EPC; ++e)
+      if (gcol + e < P.K) v[e] = __ldg(src + e);
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void store_a_chunk(unsigned char* a_img, int row, int c, const float (&v)[8]) {
+  const uint32_t off = sw128_off(row, c);
+  if constexpr (MODE == 2) {
+    __nv_bfloat162 h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    *reinterpret_cast<uint4*>(a_img + off) = *reinterpret_cast<uint4*>(h);
+  } else {
+    uint4 hi;
+    hi.x = tf32_mask(v[0]); hi.y = tf32_mask(v[1]); hi.z = tf32_mask(v[2]); hi.w = tf32_mask(v[3]);
+    *reinterpret_cast<uint4*>(a_img + off) = hi;
+    if constexpr (MODE == 0) {
+      uint4 lo;
+      lo.x = tf32_mask(v[0] - __uint_as_float(hi.x)); lo.y = tf32_mask(v[1] - __uint_as_float(hi.y));
+      lo.z = tf32_mask(v[2] - __uint_as_float(hi.z)); lo.w = tf32_mask(v[3] - __uint_as_float(hi.w));
+      *reinterpret_cast<uint4*>(a_img + TC_TILE_BYTES + off) = lo;
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __grid_constant__ TcParams prm,
+                                                                     const unsigned char* __restrict__ ws) {
+  using C = TcCfg<MODE>;
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_a[C::STAGES], full_b[C::STAGES], empty_bar[C::STAGES], accum_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- which output tile, which parts feed it
+  const int64_t m0 = (int64_t)blockIdx.x * TC_BM;
+  int part_lo = 0, part_hi = prm.n_parts, ntile = blockIdx.y, col_off = 0;
+  if (prm.combine == GS_COMBINE_CONCAT && prm.n_parts == 2) {
+    if ((int)blockIdx.y < prm.tiles_n0) part_hi = 1;
+    else { part_lo = 1; ntile = blockIdx.y - prm.tiles_n0; col_off = prm.p[0].N; }
+  }
+  const int N = prm.p[part_lo].N;
+  int total_it = 0;
+  for (int pi = part_lo; pi < part_hi; ++pi) total_it += prm.p[pi].kblocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_a[s], TC_PRODUCER_WARPS / 2);   // one arrive per warp of the producing group
+      mbar_init(&full_b[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == TC_PRODUCER_WARPS) {   // MMA warp owns the TMEM allocation
+    tmem_alloc(&tmem_base_smem, TC_BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = tmem_base_smem;
+
+  if (warp < TC_PRODUCER_WARPS) {
+    // =============================== A producers ===============================
+    // two groups of 4 warps alternate K-blocks; each thread owns 8 chunks (rows tg>>3 + 16 i, chunk tg & 7)
+    const int group = warp >> 2;
+    const int tg = threadIdx.x & 127;
+    const int c = tg & 7, r0 = tg >> 3;
+    float cur[8][8];
+    auto locate = [&](int it, int& pi, int& kb) {
+      pi = part_lo; kb = it;
+      while (kb >= prm.p[pi].kblocks) { kb -= prm.p[pi].kblocks; ++pi; }
+    };
+    auto fetch = [&](int it, float (&dst)[8][8]) {
+      int pi, kb;
+      locate(it, pi, kb);
+      const TcPart& P = prm.p[pi];
+      const bool vec = ((P.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.A) & 15u) == 0);
+      const int gcol = kb * C::BK + c * (MODE == 2 ? 8 : 4);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) load_a_chunk<MODE>(P, prm.M, m0 + r0 + 16 * i, gcol, vec, dst[i]);
+    };
+    int it = group;
+    if (it < total_it) fetch(it, cur);
+    for (; it < total_it; it += 2) {
+      const int s = it % C::STAGES;
+      const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
+      float nxt[8][8];
+      const bool more = it + 2 < total_it;
+      if (more) fetch(it + 2, nxt);                    // prefetch this group's next K-block
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      unsigned char* a_img = smem + (size_t)s * C::STAGE_BYTES;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) store_a_chunk<MODE>(a_img, r0 + 16 * i, c, cur[i]);
+      fence_proxy_async();                             // generic-proxy stores -> visible to the MMA (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_a[s]);
+      if (more) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) cur[i][e] = nxt[i][e];
+      }
+    }
+    // =============================== epilogue ===============================
+    mbar_wait(&accum_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;                           // TMEM lane quarter this warp may touch
+    const int half = warp >> 2;                       // columns [64*half, 64*half + 64)
+    const int64_t grow = m0 + q * 32 + lane;
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb) {
+      const int col0 = half * 64 + cb * 32;
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, r);
+      tmem_ld_wait();
+      if (grow < prm.M) {
+        const int gn0 = ntile * TC_BN + col0;
+        float* dst = prm.out + grow * prm.ldo + col_off + gn0;
+        const bool vec = ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) && gn0 + 32 <= N;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            v[e] = __uint_as_float(r[j + e]);
+            if (prm.bias && gn0 + j + e < N) v[e] += prm.bias[col_off + gn0 + j + e];
+            if (prm.act == GS_ACT_RELU) v[e] = fmaxf(v[e], 0.f);
+          }
+          if (vec) {
+            *reinterpret_cast<float4*>(dst + j) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (gn0 + j + e < N) dst[j + e] = v[e];
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == TC_PRODUCER_WARPS) {
+    // =============================== MMA issuer ===============================
+    constexpr uint32_t idesc = make_idesc(MODE == 2 ? 1u : 2u, TC_BM, TC_BN);
+    for (int it = 0; it < total_it; ++it) {
+      const int s = it % C::STAGES;
+      const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
+      mbar_wait(&full_a[s], ph);
+      mbar_wait(&full_b[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_base = smem_u32(smem + (size_t)s * C::STAGE_BYTES);
+        const uint32_t b_base = a_base + C::NIMG * TC_TILE_BYTES;
+        const uint64_t a_hi = make_smem_desc(a_base), b_hi = make_smem_desc(b_base);
+#pragma unroll
+        for (int k = 0; k < C::BK / C::UK; ++k) {
+          const uint64_t koff = (uint64_t)((k * 32) >> 4);          // 32 B per UMMA K step inside the swizzle atom
+          const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+          umma_ss<MODE == 2>(tmem_acc, a_hi + koff, b_hi + koff, idesc, acc);
+          if constexpr (MODE == 0) {
+            const uint64_t a_lo = make_smem_desc(a_base + TC_TILE_BYTES), b_lo = make_smem_desc(b_base + TC_TILE_BYTES);
+            umma_ss<false>(tmem_acc, a_hi + koff, b_lo + koff, idesc, 1u);
+            umma_ss<false>(tmem_acc, a_lo + koff, b_hi + koff, idesc, 1u);
+          }
+        }
+        umma_commit(&empty_bar[s]);                                  // stage reusable once these MMAs retire
+        if (it == total_it - 1) umma_commit(&accum_bar);             // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // =============================== B loader ===============================
+    if (lane == 0) {
+      int it = 0;
+      for (int pi = part_lo; pi < part_hi; ++pi) {
+        const TcPart& P = prm.p[pi];
+        const unsigned char* base = ws + P.img_off + (int64_t)ntile * P.kblocks * C::NIMG * TC_TILE_BYTES;
+        for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
+          const int s = it % C::STAGES;
+          const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_b[s], C::NIMG * TC_TILE_BYTES);
+          bulk_g2s(smem + (size_t)s * C::STAGE_BYTES + C::NIMG * TC_TILE_BYTES,
+                   base + (int64_t)kb * C::NIMG * TC_TILE_BYTES, C::NIMG * TC_TILE_BYTES, &full_b[s]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == TC_PRODUCER_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, TC_BN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int mode_of(int32_t math) { return math == GS_MATH_TF32X3 ? 0 : math == GS_MATH_TF32 ? 1 : 2; }
+
+static void fill_parts(TcParams& prm, int64_t M, const gs_gemm_part* parts, int32_t n_parts, int mode) {
+  const int BK = mode == 2 ? 64 : 32;
+  const int nimg = mode == 0 ? 2 : 1;
+  memset(&prm, 0, sizeof(prm));
+  prm.n_parts = n_parts;
+  prm.M = M;
+  int64_t off = 0;
+  for (int i = 0; i < n_parts; ++i) {
+    TcPart& P = prm.p[i];
+    P.A = parts[i].A; P.lda = parts[i].lda; P.K = parts[i].K; P.N = parts[i].N;
+    P.B = parts[i].B; P.ldb = parts[i].ldb;
+    P.kblocks = (P.K + BK - 1) / BK;
+    P.ntiles = (P.N + TC_BN - 1) / TC_BN;
+    P.img_off = off;
+    off += (int64_t)P.kblocks * P.ntiles * nimg * TC_TILE_BYTES;
+  }
+  prm.tiles_n0 = prm.p[0].ntiles;
+}
+
+int64_t sage_gemm_tc_workspace(int64_t M, const gs_gemm_part* parts, int32_t n_parts, int32_t math) {
+  TcParams prm;
+  fill_parts(prm, M, parts, n_parts, mode_of(math));
+  const TcPart& L = prm.p[n_parts - 1];
+  const int nimg = mode_of(math) == 0 ? 2 : 1;
+  return L.img_off + (int64_t)L.kblocks * L.ntiles * nimg * TC_TILE_BYTES;
+}
+
+template <int MODE>
+static int32_t launch_tc(const TcParams& prm, unsigned char* ws, cudaStream_t st) {
+  using C = TcCfg<MODE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GS_CUDA(cudaFuncSetAttribute(sage_gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  int units = prm.p[0].ntiles * prm.p[0].kblocks + (prm.n_parts == 2 ? prm.p[1].ntiles * prm.p[1].kblocks : 0);
+  pack_b_kernel<MODE><<<units, 256, 0, st>>>(prm, ws);
+  int32_t rc = launch_check("pack_b_kernel");
+  if (rc != GS_OK) return rc;
+  int tiles_n = prm.p[0].ntiles;
+  if (prm.combine == GS_COMBINE_CONCAT && prm.n_parts == 2) tiles_n += prm.p[1].ntiles;
+  dim3 grid((unsigned)((prm.M + TC_BM - 1) / TC_BM), (unsigned)tiles_n);
+  sage_gemm_tc_kernel<MODE><<<grid, TC_THREADS, C::SMEM_BYTES, st>>>(prm, ws);
+  return launch_check("sage_gemm_tc_kernel");
+}
+
+int32_t sage_gemm_tc(int64_t M, const gs_gemm_part* parts, int32_t n_parts, int32_t combine, const float* bias,
+                     int32_t act, int32_t math, float* out, int64_t ldo, void* workspace, cudaStream_t st) {
+  GS_REQUIRE(workspace != nullptr, "gs_sage_gemm: tensor-core math modes need the workspace (gs_sage_gemm_workspace_bytes)");
+  GS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 127u) == 0, "gs_sage_gemm: workspace must be 128-byte aligned");
+  const int mode = mode_of(math);
+  TcParams prm;
+  fill_parts(prm, M, parts, n_parts, mode);
+  prm.combine = combine;
+  prm.bias = bias;
+  prm.act = act;
+  prm.out = out;
+  prm.ldo = ldo;
+  unsigned char* ws = (unsigned char*)workspace;
+  if (mode == 0) return launch_tc<0>(prm, ws, st);
+  if (mode == 1) return launch_tc<1>(prm, ws, st);
+  return launch_tc<2>(prm, ws, st);
+}
+
 }  // namespace gs

@@ -52,7 +52,15 @@ class SampleAndAggregate(object):
         self.adj_info = adj
         if not torch.is_tensor(features):
             features = torch.as_tensor(features, dtype=torch.float32)
-        self.features = features.to(device=device, dtype=torch.float32).contiguous()
+        features = features.to(device=device, dtype=torch.float32)
+        F_ = features.shape[1]
+        if features.stride(1) != 1 or features.stride(0) % 4 != 0 or features.data_ptr() % 16 != 0 \
+                or features.stride(0) < ops.pad_cols(F_):
+            # re-pitch once so rows are 16-byte multiples (TMA bulk copies / 128-bit loads); keep the [N+1, F] view
+            table = torch.zeros((features.shape[0], ops.pad_cols(F_)), dtype=torch.float32, device=features.device)
+            table[:, :F_] = features
+            features = table[:, :F_]
+        self.features = features
         self.degrees = degrees
         self.concat = concat
         self.dims = [self.features.shape[1] + identity_dim]

@@ -15,6 +15,13 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _fresh_library():
+    """Rebuild libgraphsage_b200.so if any source is newer than it (no-op otherwise)."""
+    from graphsage_b200.build import build_library
+    build_library()
+
+
 def load_golden(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
 

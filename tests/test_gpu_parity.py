@@ -27,7 +27,7 @@ def dev(x, dtype=None):
     return t.cuda()
 
 
-MATHS = ["fp32"]
+MATHS = ["fp32", "tf32x3"]
 
 
 # ---------------------------------------------------------------- K1 sampler
@@ -337,3 +337,48 @@ def test_graphed_forward_matches_eager_and_oracle(gs):
     # replay from pinned host ids
     assert torch.equal(runner(torch.from_numpy(g["seeds"]).pin_memory()), eager1)
     runner.close()
+
+
+# ---------------------------------------------------------------- tcgen05 GEMM (all math modes) vs fp64
+GEMM_TOL = {"fp32": 2e-6, "tf32x3": 5e-6, "tf32": 3e-3, "bf16": 2e-2}
+
+
+@pytest.mark.parametrize("math", ["fp32", "tf32x3", "tf32", "bf16"])
+@pytest.mark.parametrize("shape", [
+    # (M, [(K, N), ...], combine, bias, act)
+    (5632, [(602, 128), (602, 128)], "concat", False, True),      # mean layer 0 at bench size
+    (512, [(256, 128), (256, 128)], "concat", False, False),      # mean layer 1
+    (5632, [(602, 256)], "add", False, True),                     # gcn layer 0
+    (300, [(50, 16), (24, 16)], "add", True, True),               # small, ragged, two K's summed
+    (1000, [(602, 512)], "add", True, True),                      # max-pool MLP Dense (bias + relu), 4 N tiles
+    (129, [(33, 200), (7, 40)], "concat", True, False),           # nothing aligned
+    (1, [(8, 8)], "add", False, False),
+])
+def test_sage_gemm_math_modes(gs, math, shape):
+    M, kn, combine, use_bias, relu = shape
+    rs = np.random.RandomState(M + len(kn))
+    code = gs.aggregators._MATH_NAMES[math]
+    parts, ref_parts = [], []
+    for (K, N) in kn:
+        lda = gs.ops.pad_cols(K) if K % 2 == 0 else K                 # exercise both aligned and unaligned pitches
+        A = torch.zeros((M, lda), dtype=torch.float32, device="cuda")
+        a = rs.randn(M, K).astype(np.float32)
+        A[:, :K] = dev(a)
+        if lda > K:
+            A[:, K:] = 1e30                                             # pad columns must never be read
+        B = rs.randn(K, N).astype(np.float32) / np.sqrt(K)
+        parts.append((A, K, dev(B)))
+        ref_parts.append(a.astype(np.float64) @ B.astype(np.float64))
+    ntot = sum(n for _, n in kn) if combine == "concat" else kn[0][1]
+    bias = rs.randn(ntot).astype(np.float32) if use_bias else None
+    ref = np.concatenate(ref_parts, axis=1) if combine == "concat" else sum(ref_parts)
+    if use_bias:
+        ref = ref + bias
+    if relu:
+        ref = np.maximum(ref, 0)
+    out = gs.ops.sage_gemm(parts, combine=gs.ops.COMBINE_CONCAT if combine == "concat" else gs.ops.COMBINE_ADD,
+                           bias=None if bias is None else dev(bias), act=gs.ops.ACT_RELU if relu else gs.ops.ACT_NONE,
+                           math=code)
+    torch.cuda.synchronize()
+    assert tuple(out.shape) == (M, ntot)
+    assert rel_err(out.cpu().numpy(), ref) < GEMM_TOL[math], (math, shape)
