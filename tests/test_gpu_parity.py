@@ -366,7 +366,7 @@ def test_sage_gemm_math_modes(gs, math, shape):
         A[:, :K] = dev(a)
         if lda > K:
             A[:, K:] = 1e30                                             # pad columns must never be read
-        B = rs.randn(K, N).astype(np.float32) / np.sqrt(K)
+        B = (rs.randn(K, N) / np.sqrt(K)).astype(np.float32)
         parts.append((A, K, dev(B)))
         ref_parts.append(a.astype(np.float64) @ B.astype(np.float64))
     ntot = sum(n for _, n in kn) if combine == "concat" else kn[0][1]
