@@ -25,6 +25,14 @@ class Segment(ctypes.Structure):
                 ("n", c_i64), ("k", c_i32), ("_pad", c_i32), ("out_row0", c_i64)]
 
 
+MAX_SHARDS = 16
+
+
+class ShardedTable(ctypes.Structure):
+    _fields_ = [("base", c_vp * MAX_SHARDS), ("n_shards", c_i32), ("my_shard", c_i32), ("rows_per_shard", c_i64),
+                ("n_global_rows", c_i64)]
+
+
 class GemmPart(ctypes.Structure):
     _fields_ = [("A", c_vp), ("lda", c_i64), ("K", c_i32), ("B", c_vp), ("ldb", c_i64), ("N", c_i32)]
 
@@ -39,6 +47,14 @@ _SIGNATURES = {
     "gs_gather_rows": (c_i32, [c_vp, c_i32, c_i64, c_i32, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "gs_gather_mean": (c_i32, [c_vp, c_i32, c_i64, c_i32, c_i64, ctypes.POINTER(Segment), c_i32, c_i32, c_vp, c_vp,
                                c_i64, c_vp]),
+    "gs_gather_mean_sharded": (c_i32, [ctypes.POINTER(ShardedTable), c_i32, c_i32, c_i64, ctypes.POINTER(Segment), c_i32,
+                                       c_i32, c_vp, c_vp, c_i64, c_vp]),
+    "gs_gather_rows_sharded": (c_i32, [ctypes.POINTER(ShardedTable), c_i32, c_i32, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "gs_shard_alloc": (c_i32, [c_i64, ctypes.POINTER(c_vp)]),
+    "gs_shard_free": (c_i32, [c_vp]),
+    "gs_ipc_export": (c_i32, [c_vp, ctypes.c_char_p]),
+    "gs_ipc_import": (c_i32, [ctypes.c_char_p, ctypes.POINTER(c_vp)]),
+    "gs_ipc_close": (c_i32, [c_vp]),
     "gs_segment_max": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i64, c_vp, c_i64, c_vp]),
     "gs_sage_gemm_workspace_bytes": (c_i64, [c_i64, ctypes.POINTER(GemmPart), c_i32, c_i32]),
     "gs_sage_gemm": (c_i32, [c_i64, ctypes.POINTER(GemmPart), c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp,

@@ -267,6 +267,89 @@ __global__ void __launch_bounds__(256) l2_normalize_kernel(float* __restrict__ x
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Node-partitioned table: the same fused gather+mean, with every row address resolved through the
+// shard table (peer-mapped pointers).  Remote rows travel over NVLink as 128-bit loads issued by
+// the consuming kernel itself - the halo exchange IS the gather.
+// ------------------------------------------------------------------------------------------
+struct ShardTab {
+  const float* base[GS_MAX_SHARDS];
+  int32_t n_shards, my_shard;
+  int64_t rows_per_shard, n_global_rows;
+};
+
+__device__ __forceinline__ const float* shard_row(const ShardTab& t, int64_t id, int64_t pitch) {
+  if (id < 0 || id >= t.n_global_rows - 1) return t.base[t.my_shard] + t.rows_per_shard * pitch;  // local zero row
+  int64_t o = id / t.rows_per_shard;
+  return t.base[o] + (id - o * t.rows_per_shard) * pitch;
+}
+
+template <int kUnroll>
+__global__ void __launch_bounds__(256) gather_mean_sharded_kernel(const __grid_constant__ ShardTab st, int F, int64_t pitch,
+                                                                  const __grid_constant__ SegTable tab, int include_self,
+                                                                  float* __restrict__ out_self,
+                                                                  float* __restrict__ out_mean, int64_t out_pitch) {
+  const int ncol4 = (int)(out_pitch >> 2);
+  for (int64_t r = blockIdx.x; r < tab.total_rows; r += gridDim.x) {
+    int64_t i;
+    const gs_segment& sg = tab.s[find_segment(tab, r, i)];
+    const int k = sg.k;
+    const int64_t orow = sg.out_row0 + i;
+    const float* srow = shard_row(st, sg.self_ids ? (int64_t)sg.self_ids[i] : sg.self_row0 + i, pitch);
+    for (int c = threadIdx.x; c < ncol4; c += blockDim.x) {
+      const int col0 = c * 4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 sv = acc;
+      if (col0 < F) {
+        int j = 0;
+        for (; j + kUnroll <= k; j += kUnroll) {
+          float4 v[kUnroll];
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            const float* p = shard_row(st, sg.neigh_ids ? (int64_t)sg.neigh_ids[i * k + j + u] : sg.neigh_row0 + i * k + j + u, pitch);
+            v[u] = ldg_nc_f4(reinterpret_cast<const float4*>(p) + c);
+          }
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+          }
+        }
+        for (; j < k; ++j) {
+          const float* p = shard_row(st, sg.neigh_ids ? (int64_t)sg.neigh_ids[i * k + j] : sg.neigh_row0 + i * k + j, pitch);
+          float4 v = ldg_nc_f4(reinterpret_cast<const float4*>(p) + c);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        if (include_self || out_self) sv = ldg_nc_f4(reinterpret_cast<const float4*>(srow) + c);
+        float div = (float)(k + (include_self ? 1 : 0));
+        if (include_self) { acc.x += sv.x; acc.y += sv.y; acc.z += sv.z; acc.w += sv.w; }
+        acc.x /= div; acc.y /= div; acc.z /= div; acc.w /= div;
+        acc = mask_tail(acc, col0, F);
+        sv = mask_tail(sv, col0, F);
+      }
+      reinterpret_cast<float4*>(out_mean + orow * out_pitch)[c] = acc;
+      if (out_self) reinterpret_cast<float4*>(out_self + orow * out_pitch)[c] = sv;
+    }
+  }
+}
+
+// one warp per row, 128-bit loads through the shard table
+__global__ void __launch_bounds__(256) gather_rows_sharded_kernel(const __grid_constant__ ShardTab st, int F, int64_t pitch,
+                                                                  const int32_t* __restrict__ ids, int64_t n,
+                                                                  float* __restrict__ out, int64_t out_pitch) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int ncol4 = (int)(out_pitch >> 2);
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const float* p = shard_row(st, ids[i], pitch);
+    for (int c = lane; c < ncol4; c += 32) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c * 4 < F) v = mask_tail(ldg_nc_f4(reinterpret_cast<const float4*>(p) + c), c * 4, F);
+      reinterpret_cast<float4*>(out + i * out_pitch)[c] = v;
+    }
+  }
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace gs
@@ -403,6 +486,116 @@ int32_t gs_l2_normalize_rows(float* x, int64_t n, int32_t C, int64_t ldx, void* 
   if (blocks > cap) blocks = cap;
   gs::l2_normalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, C, ldx);
   return gs::launch_check("l2_normalize_kernel");
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// node-partitioned table entry points
+// ---------------------------------------------------------------------------------------------
+static int32_t fill_shard_tab(const gs_sharded_table* t, gs::ShardTab& st, int64_t pitch, const char* who) {
+  GS_REQUIRE(t != nullptr, "%s: table is NULL", who);
+  GS_REQUIRE(t->n_shards >= 1 && t->n_shards <= GS_MAX_SHARDS, "%s: n_shards=%d (max %d)", who, t->n_shards, GS_MAX_SHARDS);
+  GS_REQUIRE(t->my_shard >= 0 && t->my_shard < t->n_shards, "%s: my_shard=%d", who, t->my_shard);
+  GS_REQUIRE(t->rows_per_shard > 0 && t->n_global_rows > 0 &&
+                 t->rows_per_shard * t->n_shards >= t->n_global_rows - 1,
+             "%s: rows_per_shard * n_shards must cover n_global_rows - 1", who);
+  GS_REQUIRE(pitch % 4 == 0, "%s: pitch must be a multiple of 4 floats", who);
+  memset(&st, 0, sizeof(st));
+  for (int i = 0; i < t->n_shards; ++i) {
+    GS_REQUIRE(t->base[i] != nullptr && gs::aligned16(t->base[i]), "%s: shard %d pointer NULL or not 16-byte aligned", who, i);
+    st.base[i] = (const float*)t->base[i];
+  }
+  st.n_shards = t->n_shards;
+  st.my_shard = t->my_shard;
+  st.rows_per_shard = t->rows_per_shard;
+  st.n_global_rows = t->n_global_rows;
+  return GS_OK;
+}
+
+extern "C" {
+
+int32_t gs_gather_mean_sharded(const gs_sharded_table* table_host, int32_t dtype, int32_t F, int64_t pitch,
+                               const gs_segment* segments_host, int32_t n_segments, int32_t include_self, void* out_self,
+                               void* out_mean, int64_t out_pitch, void* stream) {
+  GS_REQUIRE(dtype == GS_F32, "gs_gather_mean_sharded: only GS_F32 (dtype=%d)", dtype);
+  GS_REQUIRE(n_segments >= 0 && n_segments <= GS_MAX_SEGMENTS && (segments_host || n_segments == 0),
+             "gs_gather_mean_sharded: bad segments");
+  gs::ShardTab st;
+  int32_t rc = fill_shard_tab(table_host, st, pitch, "gs_gather_mean_sharded");
+  if (rc != GS_OK) return rc;
+  gs::SegTable tab;
+  memset(&tab, 0, sizeof(tab));
+  tab.n_segments = n_segments;
+  for (int s = 0; s < n_segments; ++s) {
+    tab.s[s] = segments_host[s];
+    GS_REQUIRE(tab.s[s].n >= 0 && tab.s[s].k >= 1, "gs_gather_mean_sharded: segment %d has n=%lld k=%d", s,
+               (long long)tab.s[s].n, tab.s[s].k);
+    tab.total_rows += tab.s[s].n;
+  }
+  if (tab.total_rows == 0) return GS_OK;
+  GS_REQUIRE(out_mean && gs::aligned16(out_mean) && (!out_self || gs::aligned16(out_self)) && out_pitch % 4 == 0 &&
+                 F > 0 && pitch >= ((F + 3) / 4) * 4 && out_pitch >= F,
+             "gs_gather_mean_sharded: bad output / pitch");
+  const int ncol4 = (int)(out_pitch / 4);
+  int threads = ((ncol4 + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  int64_t blocks = tab.total_rows;
+  int64_t cap = (int64_t)gs::sm_count() * gs::tuning("gather_ctas_per_sm", 8);
+  if (blocks > cap) blocks = cap;
+  gs::gather_mean_sharded_kernel<5><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+      st, F, pitch, tab, include_self, (float*)out_self, (float*)out_mean, out_pitch);
+  return gs::launch_check("gather_mean_sharded_kernel");
+}
+
+int32_t gs_gather_rows_sharded(const gs_sharded_table* table_host, int32_t dtype, int32_t F, int64_t pitch,
+                               const int32_t* ids, int64_t n, void* out, int64_t out_pitch, void* stream) {
+  GS_REQUIRE(dtype == GS_F32, "gs_gather_rows_sharded: only GS_F32 (dtype=%d)", dtype);
+  gs::ShardTab st;
+  int32_t rc = fill_shard_tab(table_host, st, pitch, "gs_gather_rows_sharded");
+  if (rc != GS_OK) return rc;
+  if (n == 0) return GS_OK;
+  GS_REQUIRE(ids && out && gs::aligned16(out) && out_pitch % 4 == 0 && F > 0 && pitch >= ((F + 3) / 4) * 4 && out_pitch >= F,
+             "gs_gather_rows_sharded: bad arguments");
+  int64_t blocks = (n + 7) / 8;
+  int64_t cap = (int64_t)gs::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  gs::gather_rows_sharded_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(st, F, pitch, ids, n, (float*)out,
+                                                                                      out_pitch);
+  return gs::launch_check("gather_rows_sharded_kernel");
+}
+
+int32_t gs_shard_alloc(int64_t bytes, void** dev_ptr_out) {
+  GS_REQUIRE(bytes > 0 && dev_ptr_out, "gs_shard_alloc: bad arguments");
+  GS_CUDA(cudaMalloc(dev_ptr_out, (size_t)bytes));
+  return GS_OK;
+}
+
+int32_t gs_shard_free(void* dev_ptr) {
+  if (dev_ptr) GS_CUDA(cudaFree(dev_ptr));
+  return GS_OK;
+}
+
+int32_t gs_ipc_export(const void* dev_ptr, uint8_t* handle64_out_host) {
+  GS_REQUIRE(dev_ptr && handle64_out_host, "gs_ipc_export: NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t h;
+  GS_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)));
+  memcpy(handle64_out_host, &h, 64);
+  return GS_OK;
+}
+
+int32_t gs_ipc_import(const uint8_t* handle64_host, void** dev_ptr_out) {
+  GS_REQUIRE(handle64_host && dev_ptr_out, "gs_ipc_import: NULL argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64_host, 64);
+  GS_CUDA(cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return GS_OK;
+}
+
+int32_t gs_ipc_close(void* dev_ptr) {
+  if (dev_ptr) GS_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return GS_OK;
 }
 
 }  // extern "C"

@@ -50,6 +50,10 @@ class SampleAndAggregate(object):
         self.inputs2 = self.placeholders.get("batch2")
         self.model_size = model_size
         self.adj_info = adj
+        if hasattr(features, "c_table"):                 # parallel.ShardedFeatures: node-partitioned table
+            self.features = features
+            self._finish_init(placeholders, adj, degrees, layer_infos, concat, model_size, identity_dim, device)
+            return
         if not torch.is_tensor(features):
             features = torch.as_tensor(features, dtype=torch.float32)
         features = features.to(device=device, dtype=torch.float32)
@@ -61,6 +65,9 @@ class SampleAndAggregate(object):
             table[:, :F_] = features
             features = table[:, :F_]
         self.features = features
+        self._finish_init(placeholders, adj, degrees, layer_infos, concat, model_size, identity_dim, device)
+
+    def _finish_init(self, placeholders, adj, degrees, layer_infos, concat, model_size, identity_dim, device):
         self.degrees = degrees
         self.concat = concat
         self.dims = [self.features.shape[1] + identity_dim]

@@ -88,6 +88,15 @@ def _dtype_code(t):
 
 def gather_rows(feats, ids, out=None):
     """tf.nn.embedding_lookup(features, ids) - reference graphsage/models.py:299."""
+    if hasattr(feats, "c_table"):
+        ids = _i32(ids.reshape(-1), "ids")
+        n, F = ids.numel(), feats.shape[1]
+        if out is None:
+            out = torch.empty((n, pad_cols(F)), dtype=torch.float32, device=feats.device)[:, :F]
+        check(lib().gs_gather_rows_sharded(feats.c_table(), _lib.GS_F32, F, feats.pitch, ptr(ids), n, ptr(out),
+                                           out.stride(0), stream_ptr()))
+        _launched(1 if n else 0)
+        return out
     require_cuda(feats, ids)
     if feats.dim() != 2 or feats.stride(1) != 1:
         raise ValueError("features must be a row-major 2-D tensor")
@@ -129,7 +138,10 @@ def make_segment(n, k, self_ids=None, neigh_ids=None, self_row0=0, neigh_row0=0,
 
 def gather_mean(src, segments, include_self=False, want_self=True, out_pitch=None, out_mean=None, out_self=None):
     """Fused embedding_lookup + reduce_mean over the fanout (models.py:299 + aggregators.py:48 / :106-107).
-    segments: list of Seg; returns (out_self or None, out_mean), each [rows, out_pitch]."""
+    segments: list of Seg; returns (out_self or None, out_mean), each [rows, out_pitch].
+    `src` is a float32 [rows, F] CUDA tensor, or a parallel.ShardedFeatures (node-partitioned table)."""
+    if hasattr(src, "c_table"):
+        return _gather_mean_sharded(src, segments, include_self, want_self, out_pitch, out_mean, out_self)
     require_cuda(src)
     if src.dtype != torch.float32 or src.dim() != 2 or src.stride(1) != 1:
         raise ValueError("src must be a row-major float32 2-D tensor")
@@ -146,6 +158,24 @@ def gather_mean(src, segments, include_self=False, want_self=True, out_pitch=Non
     check(lib().gs_gather_mean(ptr(src), _lib.GS_F32, src.shape[0], F, src.stride(0), arr, len(segments),
                                int(bool(include_self)), ptr(out_self) if want_self else 0, ptr(out_mean), out_pitch,
                                stream_ptr()))
+    _launched(1 if rows else 0, ev)
+    return (out_self if want_self else None), out_mean
+
+
+def _gather_mean_sharded(src, segments, include_self, want_self, out_pitch, out_mean, out_self):
+    F = src.shape[1]
+    if out_pitch is None:
+        out_pitch = pad_cols(F)
+    rows = max([s.out_row0 + s.n for s in segments] + [0])
+    if out_mean is None:
+        out_mean = torch.empty((rows, out_pitch), dtype=torch.float32, device=src.device)
+    if want_self and out_self is None:
+        out_self = torch.empty((rows, out_pitch), dtype=torch.float32, device=src.device)
+    arr = (Segment * max(len(segments), 1))(*[s.c_struct() for s in segments])
+    ev = _probe("gather_mean/%d" % rows)
+    check(lib().gs_gather_mean_sharded(src.c_table(), _lib.GS_F32, F, src.pitch, arr, len(segments),
+                                       int(bool(include_self)), ptr(out_self) if want_self else 0, ptr(out_mean),
+                                       out_pitch, stream_ptr()))
     _launched(1 if rows else 0, ev)
     return (out_self if want_self else None), out_mean
 

@@ -10,8 +10,9 @@
  * Conventions
  *   - extern "C", plain pointers and sizes, no torch types.
  *   - Pointers are DEVICE pointers unless the name ends in _host.  Row-major.  "pitch"/"ld"
- *     are in ELEMENTS.  The library never allocates or frees device memory and never
- *     synchronises: every call only enqueues work on `stream` (a cudaStream_t passed as void*).
+ *     are in ELEMENTS.  The library never synchronises: every call only enqueues work on `stream`
+ *     (a cudaStream_t passed as void*).  It never allocates device memory either, with one exception:
+ *     gs_shard_alloc/gs_shard_free (cudaMalloc'd buffers that can be exported through CUDA IPC).
  *   - Return value: 0 = OK, <0 = gs_status error; gs_last_error_string() (thread-local, host)
  *     describes the last failure.  No exceptions cross the boundary.
  *   - There is no CPU fallback: without a CUDA device every compute entry returns GS_ERR_CUDA.
@@ -114,6 +115,39 @@ typedef struct {
 int32_t gs_gather_mean(const void* src, int32_t dtype, int64_t n_src_rows, int32_t F, int64_t pitch,
                        const gs_segment* segments_host, int32_t n_segments, int32_t include_self,
                        void* out_self, void* out_mean, int64_t out_pitch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Node-partitioned feature table (multi-GPU; no reference counterpart - the reference is
+ * single-device).  Rank r owns global rows [r*rows_per_shard, (r+1)*rows_per_shard); every rank maps all
+ * shards into its address space (CUDA IPC over NVLink/NVSwitch), so the gather kernel resolves
+ *   row(id) = base[id / rows_per_shard] + (id % rows_per_shard) * pitch
+ * and pulls remote rows with plain 128-bit loads: the halo exchange is fused into the gather, no
+ * staging buffer, no collective on the data path.  Ids outside [0, n_global_rows-1) - including the
+ * dummy id N - read the caller's local zero row (index rows_per_shard of its own shard).
+ * gs_gather_mean_sharded has the semantics of gs_gather_mean with `src` replaced by the table.
+ * --------------------------------------------------------------------------------------------- */
+#define GS_MAX_SHARDS 16
+typedef struct {
+  const void* base[GS_MAX_SHARDS]; /* device pointers, shard r = [rows_per_shard + 1, pitch] */
+  int32_t n_shards;
+  int32_t my_shard;
+  int64_t rows_per_shard;
+  int64_t n_global_rows;           /* N + 1 (the dummy row is virtual: every shard carries its own zero row) */
+} gs_sharded_table;
+
+int32_t gs_gather_mean_sharded(const gs_sharded_table* table_host, int32_t dtype, int32_t F, int64_t pitch,
+                               const gs_segment* segments_host, int32_t n_segments, int32_t include_self,
+                               void* out_self, void* out_mean, int64_t out_pitch, void* stream);
+int32_t gs_gather_rows_sharded(const gs_sharded_table* table_host, int32_t dtype, int32_t F, int64_t pitch,
+                               const int32_t* ids, int64_t n, void* out, int64_t out_pitch, void* stream);
+
+/* Shard buffers are allocated by the library with cudaMalloc so that they can be exported through
+ * CUDA IPC (the only allocation the library ever makes; freed by gs_shard_free). */
+int32_t gs_shard_alloc(int64_t bytes, void** dev_ptr_out);
+int32_t gs_shard_free(void* dev_ptr);
+int32_t gs_ipc_export(const void* dev_ptr, uint8_t* handle64_out_host);
+int32_t gs_ipc_import(const uint8_t* handle64_host, void** dev_ptr_out);
+int32_t gs_ipc_close(void* dev_ptr);
 
 /* segmented max over fixed fanout: out[i, c] = max_j x[i*k + j, c]   (aggregators.py:182) */
 int32_t gs_segment_max(const float* x, int64_t n, int32_t k, int32_t C, int64_t ldx,
