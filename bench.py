@@ -76,9 +76,26 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def build_graph():
+def build_graph(rank=0, world=1, barrier=None):
+    """Reddit-shape synthetic graph (seed 123).  With several ranks, rank 0 generates it once and the
+    others read it from /dev/shm (same bytes everywhere)."""
     from graphsage_b200.synthetic import reddit_like
-    return reddit_like(n=N_NODES, f=F, max_degree=MAX_DEG, seed=123)
+    if world == 1:
+        return reddit_like(n=N_NODES, f=F, max_degree=MAX_DEG, seed=123)
+    base = "/dev/shm/gs_b200_graph_%d" % os.getuid()
+    if rank == 0:
+        g = reddit_like(n=N_NODES, f=F, max_degree=MAX_DEG, seed=123)
+        np.save(base + "_adj.npy", g["adj"])
+        np.save(base + "_feat.npy", g["features"])
+    barrier()
+    if rank != 0:
+        g = dict(adj=np.load(base + "_adj.npy"), features=np.load(base + "_feat.npy"), n=N_NODES, f=F,
+                 max_degree=MAX_DEG)
+    barrier()
+    if rank == 0:
+        os.remove(base + "_adj.npy")
+        os.remove(base + "_feat.npy")
+    return g
 
 
 def make_weights(kind, rs):
@@ -136,8 +153,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--aggregator", default="mean", choices=["mean", "gcn"])
-    ap.add_argument("--math", default=os.environ.get("GS_MATH", "fp32"))
+    ap.add_argument("--math", default=os.environ.get("GS_MATH", "tf32x3"),
+                    help="tf32x3 (tcgen05, fp32-grade: meets the 1e-4 parity bar) | fp32 (CUDA cores) | tf32 | bf16")
     ap.add_argument("--cpu-batches", type=int, default=12)
+    ap.add_argument("--no-partitioned", action="store_true", help="skip the node-partitioned measurement at N > 1")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -177,7 +196,7 @@ def main():
     import graphsage_b200 as gs
     from graphsage_b200 import ops
 
-    g = build_graph()
+    g = build_graph(rank, world, (lambda: dist.barrier()) if dist is not None else None)
     dev = torch.device("cuda", local_rank)
     table = torch.zeros((N_NODES + 1, ops.pad_cols(F)), dtype=torch.float32, device=dev)
     table[:, :F] = torch.from_numpy(g["features"]).to(dev)
@@ -189,16 +208,6 @@ def main():
     model = gs.SampleAndAggregate({"batch_size": BATCH, "dropout": 0.}, table[:, :F], adj_dev, None, infos,
                                   concat=(kind == "mean"), aggregator_type=kind, device=dev)
     weights = make_weights(kind, np.random.RandomState(7))
-    # weak scaling: every rank holds a replica of the 561 MB table and runs its own seed batches
-    rs = np.random.RandomState(1000 + rank)
-    total = args.warmup + args.steps
-    seeds_host = torch.from_numpy(rs.randint(0, N_NODES, size=(total, BATCH)).astype(np.int32)).pin_memory()
-    seeds_dev = seeds_host.to(dev)
-    out_host = torch.empty((args.steps, BATCH, 2 * DIM), dtype=torch.float32).pin_memory()
-    model.forward(seeds_dev[0])                       # creates the aggregators
-    for a, w in zip(model.aggregators, weights):
-        for k_, v in w.items():
-            a.vars[k_] = torch.from_numpy(v).to(dev)
 
     def barrier():
         if dist is not None:
@@ -212,58 +221,95 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    total = args.warmup + args.steps
     probe_name = "gather_mean/%d" % (BATCH * 11)
-    runner = model.graphed(BATCH, normalize=True, probe=probe_name)     # CUDA-graph replay of forward()
 
-    # ---- device-resident timing ("value"): inputs already in HBM
-    for i in range(args.warmup):
-        runner(seeds_dev[i])
-    barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    probe_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        out = runner(seeds_dev[args.warmup + i], probe_events=probe_events[i])
-    e1.record()
-    barrier()
-    launches = runner.launches_per_replay * args.steps
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    probe = {probe_name: probe_events}
-    clk = clocks.summary()
-    value = world * BATCH * args.steps / (ms_total * 1e-3)
+    def measure(mdl, lo, hi, tag):
+        """value (ids resident in HBM) and e2e (pinned-host ids in, result to pinned host) for one model."""
+        rs = np.random.RandomState(1000 + rank)
+        seeds_host = torch.from_numpy(rs.randint(lo, hi, size=(total, BATCH)).astype(np.int32)).pin_memory()
+        seeds_dev = seeds_host.to(dev)
+        out_host = torch.empty((args.steps, BATCH, 2 * DIM), dtype=torch.float32).pin_memory()
+        mdl.forward(seeds_dev[0])                       # creates the aggregators
+        for a, w in zip(mdl.aggregators, weights):
+            for k_, v in w.items():
+                a.vars[k_] = torch.from_numpy(v).to(dev)
+        runner = mdl.graphed(BATCH, normalize=True, probe=probe_name)     # CUDA-graph replay of forward()
+        for i in range(args.warmup):
+            runner(seeds_dev[i])
+        barrier()
+        clocks = ClockSampler(local_rank)
+        clocks.start()
+        pev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            out = runner(seeds_dev[args.warmup + i], probe_events=pev[i])
+        e1.record()
+        barrier()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        clk = clocks.summary()
+        for i in range(min(args.warmup, 5)):
+            runner(seeds_host[i])
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            out = runner(seeds_host[args.warmup + i])          # pinned host ids -> device (async copy on the stream)
+            out_host[i].copy_(out, non_blocking=True)          # result -> pinned host
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        chk = float(out_host[-1].abs().sum())                  # the host really received the last result
+        assert np.isfinite(chk) and chk > 0
+        kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in pev]))
+        res = dict(ms_total=ms_total, ms_e2e=ms_e2e, clocks=clk, launches=runner.launches_per_replay * args.steps,
+                   gather_kernel_ms=max_over_ranks(kernel_ms), value=world * BATCH * args.steps / (ms_total * 1e-3),
+                   e2e=world * BATCH * args.steps / (ms_e2e * 1e-3))
+        runner.close()
+        return res
 
-    # ---- end-to-end through the public API with host buffers (H2D of ids, D2H of the result, every step)
-    for i in range(min(args.warmup, 5)):
-        runner(seeds_host[i])
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        out = runner(seeds_host[args.warmup + i])          # pinned host ids -> device (async copy on the stream)
-        out_host[i].copy_(out, non_blocking=True)          # result -> pinned host
-    e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    e2e_value = world * BATCH * args.steps / (ms_e2e * 1e-3)
-    check = float(out_host[-1].abs().sum())                # the host really received the last result
-    assert np.isfinite(check) and check > 0
+    # replicated table: every rank holds the 561 MB table and runs its own seed batches (no data-path collective)
+    rep = measure(model, 0, N_NODES, "replicated")
+    ms_total, ms_e2e, clk, launches = rep["ms_total"], rep["ms_e2e"], rep["clocks"], rep["launches"]
+    value, e2e_value = rep["value"], rep["e2e"]
+    probe = None
+
+    # node-partitioned table with the halo exchange fused into the gather (peer loads over NVLink); owner-computes seeds
+    part = None
+    if world > 1 and not args.no_partitioned:
+        from graphsage_b200 import parallel
+        R = parallel.rows_per_shard(N_NODES, world)
+        lo, hi = rank * R, min(N_NODES, (rank + 1) * R)
+        shard = parallel.ShardedFeatures(g["features"][lo:hi], N_NODES)
+        sampler_p = gs.UniformNeighborSampler(adj_dev, seed=123)
+        infos_p = [gs.SAGEInfo("node", sampler_p, FANOUT[0], dims[0]), gs.SAGEInfo("node", sampler_p, FANOUT[1], dims[1])]
+        model_p = gs.SampleAndAggregate({"batch_size": BATCH, "dropout": 0.}, shard, adj_dev, None, infos_p,
+                                        concat=(kind == "mean"), aggregator_type=kind, device=dev)
+        pr = measure(model_p, lo, hi, "partitioned")
+        rs = np.random.RandomState(1000 + rank)
+        smp, _ = model_p.sample(torch.from_numpy(rs.randint(lo, hi, size=BATCH).astype(np.int32)).to(dev), infos_p)
+        rho = max_over_ranks(shard.remote_fraction(torch.cat(smp)))
+        part = {"value": pr["value"], "unit": "nodes/s", "ms_per_step": pr["ms_total"] / args.steps,
+                "e2e": pr["e2e"], "remote_row_fraction_max": rho, "gather_kernel_ms": pr["gather_kernel_ms"],
+                "nvlink_GBps_per_gpu": rho * GATHER_BYTES / (pr["gather_kernel_ms"] * 1e-3) / 1e9,
+                "note": "node-partitioned features (contiguous community-aligned ranges), adjacency replicated, "
+                        "remote rows pulled by the gather kernel over NVLink peer mappings; owner-computes seeds"}
+        barrier()
+        shard.close()
 
     if rank != 0:
         return
     # ---- roofline of the dominant kernel: the layer-0 fused gather+mean
     peak, peak_src = peaks()
-    key = probe_name
-    durs = [a.elapsed_time(b) for a, b in probe.get(key, [])]
     roof = None
-    if durs:
-        avg_ms = float(np.mean(durs))
+    if rep["gather_kernel_ms"] > 0:
+        avg_ms = rep["gather_kernel_ms"]
         achieved = GATHER_BYTES / (avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "gather_mean (layer 0, hops 0+1)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "avg_kernel_ms": avg_ms, "algorithmic_bytes_per_launch": GATHER_BYTES,
                 "kernel_share_of_step": avg_ms / (ms_total / args.steps)}
-    kernel_ms = {k_: float(np.mean([a.elapsed_time(b) for a, b in v])) for k_, v in probe.items()}
+    kernel_ms = {probe_name: rep["gather_kernel_ms"]}
     cpu = None
     if world == 1 and args.cpu_batches > 0:
         rate, cores, med = cpu_reference_rate(g, kind, weights, args.cpu_batches, 2, np.random.RandomState(1000))
@@ -278,7 +324,8 @@ def main():
                    "l2": "inputs larger than L2 (567 MB feature table vs 126 MB L2; fresh random seeds every step)"},
         "e2e": {"value": e2e_value, "unit": "nodes/s", "h2d_bytes_per_step": BATCH * 4,
                 "d2h_bytes_per_step": BATCH * 2 * DIM * 4, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "kernel_ms": kernel_ms}))
+        "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "kernel_ms": kernel_ms,
+        "partitioned": part}))
 
 
 if __name__ == "__main__":

@@ -175,7 +175,7 @@ class MaxPoolingAggregator(_SageAggregator):
     def aggregate_rows(self, src, segments):
         rows = max(s.out_row0 + s.n for s in segments)
         dev = src.device
-        xs = torch.empty((rows, src.shape[1]), dtype=torch.float32, device=dev)
+        xs = torch.empty((rows, ops.pad_cols(src.shape[1])), dtype=torch.float32, device=dev)[:, :src.shape[1]]
         hmax = torch.empty((rows, self.hidden_dim), dtype=torch.float32, device=dev)
         for s in segments:
             n, k = s.n, s.k

@@ -37,10 +37,16 @@ def community_graph_csr(n, n_comm=41, mean_deg=50, p_in=0.8, seed=123, max_deg_c
     return indptr, b, comm
 
 
-def reddit_like(n=232965, f=602, max_degree=128, seed=123, with_features=True, mean_deg=50):
+def reddit_like(n=232965, f=602, max_degree=128, seed=123, with_features=True, mean_deg=50, locality=True):
     """Returns dict(indptr, indices, adj[n+1, max_degree] int32, deg, comm, features[n+1, f] fp32 with zero last row)."""
     from .minibatch import padded_from_csr_fast
+    from .parallel import locality_order, relabel_graph
     indptr, indices, comm = community_graph_csr(n, mean_deg=mean_deg, seed=seed)
+    if locality:
+        # rename nodes so communities are contiguous id ranges (what a locality-aware node partition wants)
+        order, inv = locality_order(comm)
+        indptr, indices = relabel_graph(indptr, indices, order, inv)
+        comm = comm[order]
     adj, deg = padded_from_csr_fast(indptr, indices, max_degree, seed=seed)
     out = dict(indptr=indptr, indices=indices, adj=adj, deg=deg, comm=comm, n=n, f=f, max_degree=max_degree)
     if with_features:

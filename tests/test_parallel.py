@@ -1,0 +1,175 @@
+"""Multi-process tests of the node-partitioned path.
+CPU (gloo, world_size 2): partition arithmetic, owner-computes seed routing, locality relabelling.
+GPU (nccl, 2 GPUs, skipped on a 1-GPU box): partitioned forward over peer-mapped shards == single-GPU forward."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, rel_err  # noqa: F401
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _init(rank, world, port, backend):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    if backend == "nccl":
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+
+
+def _cpu_worker(rank, world, port, q):
+    try:
+        from graphsage_b200 import parallel
+        _init(rank, world, port, "gloo")
+        n_nodes = 1001
+        R = parallel.rows_per_shard(n_nodes, world)
+        assert R == 501
+        rs = np.random.RandomState(rank)
+        seeds = torch.from_numpy(rs.randint(0, n_nodes, size=300 + 17 * rank).astype(np.int32))
+        mine = parallel.route_seeds(seeds, n_nodes)
+        assert mine.dtype == torch.int32
+        own = parallel.owner_of(mine, n_nodes, world)
+        assert bool((own == rank).all())
+        # nothing lost, nothing duplicated: gather every rank's routed seeds and compare multisets
+        got, sent = [None] * world, [None] * world
+        dist.all_gather_object(got, mine.tolist())
+        dist.all_gather_object(sent, seeds.tolist())
+        assert sorted(sum(got, [])) == sorted(sum(sent, []))
+        # dummy / out-of-range ids have no owner
+        assert parallel.owner_of(np.array([n_nodes, -1, 0, n_nodes - 1]), n_nodes, world).tolist() == [-1, -1, 0, world - 1]
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def _run(worker, world, *args):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=worker, args=(r, world, port, q) + args) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in res:
+        assert msg == "ok", "rank %d failed:\n%s" % (rank, msg)
+
+
+def test_route_seeds_gloo_world2():
+    _run(_cpu_worker, 2)
+
+
+def test_locality_relabel_preserves_graph():
+    from graphsage_b200 import parallel
+    from graphsage_b200.synthetic import community_graph_csr
+    indptr, indices, comm = community_graph_csr(2000, n_comm=7, mean_deg=12, seed=3)
+    order, inv = parallel.locality_order(comm)
+    assert (np.diff(comm[order]) >= 0).all()                      # communities are contiguous in the new labelling
+    p2, i2 = parallel.relabel_graph(indptr, indices, order, inv)
+    assert p2[-1] == indptr[-1]
+    for new in range(0, 2000, 97):
+        old = order[new]
+        want = sorted(inv[indices[indptr[old]:indptr[old + 1]]].tolist())
+        assert sorted(i2[p2[new]:p2[new + 1]].tolist()) == want
+    # locality: with a contiguous 4-way split most neighbours share their node's part
+    R = parallel.rows_per_shard(2000, 4)
+    src = np.repeat(np.arange(2000), np.diff(p2))
+    assert ((src // R) == (i2 // R)).mean() > 0.6
+
+
+def _gpu_worker(rank, world, port, q):
+    try:
+        _init(rank, world, port, "nccl")
+        import graphsage_b200 as gs
+        from graphsage_b200 import parallel
+        rs = np.random.RandomState(0)                      # identical on every rank
+        n, md, f, B = 3001, 32, 602, 64
+        adj = rs.randint(0, n, size=(n + 1, md)).astype(np.int32)
+        adj[n] = n
+        adj[5] = n                                         # an isolated node -> dummy neighbours
+        feats = rs.randn(n, f).astype(np.float32)
+        seeds = rs.randint(0, n, size=B).astype(np.int32)
+        seeds[0] = 5
+        dev = torch.device("cuda", rank)
+        R = parallel.rows_per_shard(n, world)
+        lo, hi = rank * R, min(n, (rank + 1) * R)
+        shard = parallel.ShardedFeatures(feats[lo:hi], n)
+        adj_dev = torch.from_numpy(adj).to(dev)
+        full = torch.from_numpy(np.vstack([feats, np.zeros((1, f), np.float32)])).to(dev)
+        outs = {}
+        for kind, concat, dim in (("mean", True, 128), ("gcn", False, 256), ("maxpool", True, 32)):
+            res = []
+            for table in (shard, full):
+                gs.inits.manual_seed(7, dev)
+                sampler = gs.UniformNeighborSampler(adj_dev, seed=123)
+                infos = [gs.SAGEInfo("node", sampler, 25, dim), gs.SAGEInfo("node", sampler, 10, dim)]
+                m = gs.SampleAndAggregate({"batch_size": B, "dropout": 0.}, table, adj_dev, None, infos, concat=concat,
+                                          aggregator_type=kind, device=dev)
+                res.append(m.forward(torch.from_numpy(seeds), normalize=True).cpu().numpy())
+            assert np.array_equal(res[0], res[1]), "partitioned != single-table for %s (max diff %g)" % (
+                kind, np.abs(res[0] - res[1]).max())
+            outs[kind] = res[0]
+        ids = torch.from_numpy(rs.randint(0, n + 1, size=5000).astype(np.int32)).to(dev)
+        rows = gs.ops.gather_rows(shard, ids)
+        assert torch.equal(rows, full[ids.long()])
+        frac = shard.remote_fraction(ids)
+        assert 0.3 < frac < 0.7
+        shard.close()
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_partitioned_forward_two_gpus():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    _run(_gpu_worker, 2)
+
+
+@pytest.mark.gpu
+def test_sharded_table_single_rank_matches_dense():
+    """world_size 1: the sharded kernels with one shard must reproduce the dense-table kernels exactly."""
+    import graphsage_b200 as gs
+    from graphsage_b200 import parallel
+    rs = np.random.RandomState(1)
+    n, f = 2000, 602
+    feats = rs.randn(n, f).astype(np.float32)
+    shard = parallel.ShardedFeatures(feats, n)
+    full = torch.from_numpy(np.vstack([feats, np.zeros((1, f), np.float32)])).cuda()
+    ids = torch.from_numpy(rs.randint(-3, n + 5, size=4000).astype(np.int32)).cuda()
+    clamp = ids.clone().long()
+    clamp[(clamp < 0) | (clamp >= n)] = n
+    assert torch.equal(gs.ops.gather_rows(shard, ids), full[clamp])
+    s0 = torch.from_numpy(rs.randint(0, n, size=40).astype(np.int32)).cuda()
+    s1 = torch.from_numpy(rs.randint(0, n + 1, size=400).astype(np.int32)).cuda()
+    seg = [gs.ops.Seg(40, 10, self_ids=s0, neigh_ids=s1)]
+    a = gs.ops.gather_mean(shard, seg, include_self=True)
+    gs._lib.set_tuning("gather_variant", 0)
+    b = gs.ops.gather_mean(full, seg, include_self=True)
+    gs._lib.set_tuning("gather_variant", 1)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    shard.close()
