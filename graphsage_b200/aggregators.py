@@ -36,8 +36,28 @@ def _dense_segment(n, k):
 class _SageAggregator(Layer):
     def _finish(self, parts, combine):
         code, post = act_code(self.act)
-        y = ops.sage_gemm(parts, combine=combine, bias=self.vars.get("bias"), act=code, math=self.math)
+        if getattr(self, "_packed", None) is None:
+            self._packed = ops.PackedWeights()
+        y = ops.sage_gemm(parts, combine=combine, bias=self.vars.get("bias"), act=code, math=self.math,
+                          packed=self._packed)
         return post(y) if post else y
+
+    def _small_layer(self, src, segments, parts, combine, include_self, final):
+        """Whole layer in one launch when it is small (last layers: B rows).  Returns None if not applicable."""
+        code, post = act_code(self.act)
+        if (len(segments) != 1 or not torch.is_tensor(src) or post is not None or self.dropout
+                or segments[0].out_row0 + segments[0].n > ops.SMALL_LAYER_MAX_ROWS or src.shape[1] > 2048
+                or any(K != src.shape[1] for (_, K, _) in parts)):
+            return None
+        l2 = bool(final and final.get("l2_normalize"))
+        bump = final.get("bump") if final else None
+        y = ops.sage_layer_small(src, segments[0], parts, combine=combine, include_self=include_self,
+                                 bias=self.vars.get("bias"), act=code, l2_normalize=l2,
+                                 counter_dev=None if bump is None else bump[0], counter_inc=0 if bump is None else bump[1])
+        if final is not None:
+            final["normalized"] = l2
+            final["bumped"] = bump is not None
+        return y
 
     @property
     def output_width(self):
@@ -77,9 +97,14 @@ class MeanAggregator(_SageAggregator):
         return self._finish([(self_vecs, self.input_dim, self.vars["self_weights"]),
                              (means, self.neigh_input_dim, self.vars["neigh_weights"])], self._combine())
 
-    def aggregate_rows(self, src, segments):
+    def aggregate_rows(self, src, segments, final=None):
         if self.dropout:
             raise NotImplementedError("dropout > 0 uses the dense call path")
+        y = self._small_layer(src, segments, [(None, self.input_dim, self.vars["self_weights"]),
+                                              (None, self.neigh_input_dim, self.vars["neigh_weights"])],
+                              self._combine(), False, final)
+        if y is not None:
+            return y
         xs, xm = ops.gather_mean(src, segments, want_self=True)
         return self._finish([(xs, self.input_dim, self.vars["self_weights"]),
                              (xm, self.neigh_input_dim, self.vars["neigh_weights"])], self._combine())
@@ -118,9 +143,13 @@ class GCNAggregator(_SageAggregator):
         _, means = ops.gather_mean(src, seg, include_self=True, want_self=False)
         return self._finish([(means, self.neigh_input_dim, self.vars["weights"])], ops.COMBINE_ADD)
 
-    def aggregate_rows(self, src, segments):
+    def aggregate_rows(self, src, segments, final=None):
         if self.dropout:
             raise NotImplementedError("dropout > 0 uses the dense call path")
+        y = self._small_layer(src, segments, [(None, self.neigh_input_dim, self.vars["weights"])], ops.COMBINE_ADD, True,
+                              final)
+        if y is not None:
+            return y
         _, means = ops.gather_mean(src, segments, include_self=True, want_self=False)
         return self._finish([(means, self.neigh_input_dim, self.vars["weights"])], ops.COMBINE_ADD)
 
@@ -172,7 +201,7 @@ class MaxPoolingAggregator(_SageAggregator):
         return self._finish([(self_vecs, self.input_dim, self.vars["self_weights"]),
                              (hmax, self.hidden_dim, self.vars["neigh_weights"])], self._combine())
 
-    def aggregate_rows(self, src, segments):
+    def aggregate_rows(self, src, segments, final=None):
         rows = max(s.out_row0 + s.n for s in segments)
         dev = src.device
         xs = torch.empty((rows, ops.pad_cols(src.shape[1])), dtype=torch.float32, device=dev)[:, :src.shape[1]]

@@ -6,7 +6,8 @@ int32_t sage_gemm_simt(int64_t M, const gs_gemm_part* parts, int32_t n_parts, in
                        int32_t act, float* out, int64_t ldo, cudaStream_t st);
 int64_t sage_gemm_tc_workspace(int64_t M, const gs_gemm_part* parts, int32_t n_parts, int32_t math);
 int32_t sage_gemm_tc(int64_t M, const gs_gemm_part* parts, int32_t n_parts, int32_t combine, const float* bias,
-                     int32_t act, int32_t math, float* out, int64_t ldo, void* workspace, cudaStream_t st);
+                     int32_t act, int32_t math, float* out, int64_t ldo, const void* workspace, cudaStream_t st);
+int32_t sage_gemm_tc_pack(const gs_gemm_part* parts, int32_t n_parts, int32_t math, void* workspace, cudaStream_t st);
 }  // namespace gs
 
 static int32_t check_parts(int64_t M, const gs_gemm_part* parts, int32_t n_parts, int32_t combine) {
@@ -31,8 +32,19 @@ int64_t gs_sage_gemm_workspace_bytes(int64_t M, const gs_gemm_part* parts_host, 
   return gs::sage_gemm_tc_workspace(M, parts_host, n_parts, math);
 }
 
-int32_t gs_sage_gemm(int64_t M, const gs_gemm_part* parts_host, int32_t n_parts, int32_t combine, const float* bias,
-                     int32_t act, int32_t math, float* out, int64_t ldo, void* workspace, void* stream) {
+static bool is_tc(int32_t math) { return math == GS_MATH_TF32X3 || math == GS_MATH_TF32 || math == GS_MATH_BF16; }
+
+int32_t gs_sage_gemm_pack(const gs_gemm_part* parts_host, int32_t n_parts, int32_t math, void* workspace, void* stream) {
+  int32_t rc = check_parts(1, parts_host, n_parts, GS_COMBINE_CONCAT);
+  if (rc != GS_OK) return rc;
+  if (math == GS_MATH_FP32_SIMT) return GS_OK;      // nothing to pack
+  GS_REQUIRE(is_tc(math), "gs_sage_gemm_pack: unknown math mode %d", math);
+  return gs::sage_gemm_tc_pack(parts_host, n_parts, math, workspace, (cudaStream_t)stream);
+}
+
+int32_t gs_sage_gemm_prepacked(int64_t M, const gs_gemm_part* parts_host, int32_t n_parts, int32_t combine,
+                               const float* bias, int32_t act, int32_t math, float* out, int64_t ldo,
+                               const void* workspace, void* stream) {
   int32_t rc = check_parts(M, parts_host, n_parts, combine);
   if (rc != GS_OK) return rc;
   if (M == 0) return GS_OK;
@@ -42,10 +54,17 @@ int32_t gs_sage_gemm(int64_t M, const gs_gemm_part* parts_host, int32_t n_parts,
   GS_REQUIRE(act == GS_ACT_NONE || act == GS_ACT_RELU, "gs_sage_gemm: act=%d", act);
   if (math == GS_MATH_FP32_SIMT)
     return gs::sage_gemm_simt(M, parts_host, n_parts, combine, bias, act, out, ldo, (cudaStream_t)stream);
-  if (math == GS_MATH_TF32X3 || math == GS_MATH_TF32 || math == GS_MATH_BF16)
-    return gs::sage_gemm_tc(M, parts_host, n_parts, combine, bias, act, math, out, ldo, workspace, (cudaStream_t)stream);
-  gs::set_error("gs_sage_gemm: unknown math mode %d", math);
-  return GS_ERR_INVALID_ARG;
+  GS_REQUIRE(is_tc(math), "gs_sage_gemm: unknown math mode %d", math);
+  return gs::sage_gemm_tc(M, parts_host, n_parts, combine, bias, act, math, out, ldo, workspace, (cudaStream_t)stream);
+}
+
+int32_t gs_sage_gemm(int64_t M, const gs_gemm_part* parts_host, int32_t n_parts, int32_t combine, const float* bias,
+                     int32_t act, int32_t math, float* out, int64_t ldo, void* workspace, void* stream) {
+  if (M > 0 && math != GS_MATH_FP32_SIMT) {
+    int32_t rc = gs_sage_gemm_pack(parts_host, n_parts, math, workspace, stream);
+    if (rc != GS_OK) return rc;
+  }
+  return gs_sage_gemm_prepacked(M, parts_host, n_parts, combine, bias, act, math, out, ldo, workspace, stream);
 }
 
 }  // extern "C"

@@ -438,17 +438,20 @@ int64_t sage_gemm_tc_workspace(int64_t M, const gs_gemm_part* parts, int32_t n_p
 }
 
 template <int MODE>
-static int32_t launch_tc(const TcParams& prm, unsigned char* ws, cudaStream_t st) {
+static int32_t launch_pack(const TcParams& prm, unsigned char* ws, cudaStream_t st) {
+  int units = prm.p[0].ntiles * prm.p[0].kblocks + (prm.n_parts == 2 ? prm.p[1].ntiles * prm.p[1].kblocks : 0);
+  pack_b_kernel<MODE><<<units, 256, 0, st>>>(prm, ws);
+  return launch_check("pack_b_kernel");
+}
+
+template <int MODE>
+static int32_t launch_tc(const TcParams& prm, const unsigned char* ws, cudaStream_t st) {
   using C = TcCfg<MODE>;
   static bool attr_set = false;
   if (!attr_set) {
     GS_CUDA(cudaFuncSetAttribute(sage_gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  int units = prm.p[0].ntiles * prm.p[0].kblocks + (prm.n_parts == 2 ? prm.p[1].ntiles * prm.p[1].kblocks : 0);
-  pack_b_kernel<MODE><<<units, 256, 0, st>>>(prm, ws);
-  int32_t rc = launch_check("pack_b_kernel");
-  if (rc != GS_OK) return rc;
   int tiles_n = prm.p[0].ntiles;
   if (prm.combine == GS_COMBINE_CONCAT && prm.n_parts == 2) tiles_n += prm.p[1].ntiles;
   dim3 grid((unsigned)((prm.M + TC_BM - 1) / TC_BM), (unsigned)tiles_n);
@@ -456,8 +459,20 @@ static int32_t launch_tc(const TcParams& prm, unsigned char* ws, cudaStream_t st
   return launch_check("sage_gemm_tc_kernel");
 }
 
+int32_t sage_gemm_tc_pack(const gs_gemm_part* parts, int32_t n_parts, int32_t math, void* workspace, cudaStream_t st) {
+  GS_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 127u) == 0,
+             "gs_sage_gemm_pack: workspace must be non-NULL and 128-byte aligned");
+  const int mode = mode_of(math);
+  TcParams prm;
+  fill_parts(prm, 0, parts, n_parts, mode);
+  unsigned char* ws = (unsigned char*)workspace;
+  if (mode == 0) return launch_pack<0>(prm, ws, st);
+  if (mode == 1) return launch_pack<1>(prm, ws, st);
+  return launch_pack<2>(prm, ws, st);
+}
+
 int32_t sage_gemm_tc(int64_t M, const gs_gemm_part* parts, int32_t n_parts, int32_t combine, const float* bias,
-                     int32_t act, int32_t math, float* out, int64_t ldo, void* workspace, cudaStream_t st) {
+                     int32_t act, int32_t math, float* out, int64_t ldo, const void* workspace, cudaStream_t st) {
   GS_REQUIRE(workspace != nullptr, "gs_sage_gemm: tensor-core math modes need the workspace (gs_sage_gemm_workspace_bytes)");
   GS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 127u) == 0, "gs_sage_gemm: workspace must be 128-byte aligned");
   const int mode = mode_of(math);
@@ -468,7 +483,7 @@ int32_t sage_gemm_tc(int64_t M, const gs_gemm_part* parts, int32_t n_parts, int3
   prm.act = act;
   prm.out = out;
   prm.ldo = ldo;
-  unsigned char* ws = (unsigned char*)workspace;
+  const unsigned char* ws = (const unsigned char*)workspace;
   if (mode == 0) return launch_tc<0>(prm, ws, st);
   if (mode == 1) return launch_tc<1>(prm, ws, st);
   return launch_tc<2>(prm, ws, st);

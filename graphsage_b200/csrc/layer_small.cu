@@ -1,0 +1,177 @@
+// One whole aggregator layer for a small number of output rows in a single launch (exact fp32 FFMA):
+//   mean over the fanout -> self/neigh matmuls -> add | concat -> bias -> act -> row l2_normalize
+//   reference graphsage/aggregators.py:43-64 (mean), :101-116 (gcn), graphsage/models.py:368.
+// The last layers of the recursion have only B rows (512): a tensor-core tile pipeline is all
+// latency there, and three or four launches cost more than the math.  Each CTA owns kRows output
+// rows end to end, so the row norm is CTA-local.  Weights stream from L2 (they are shared by all CTAs).
+#include "common.cuh"
+
+namespace gs {
+
+constexpr int LS_ROWS = 4;
+constexpr int LS_THREADS = 256;
+
+struct LsParams {
+  const float* src;
+  int64_t n_src_rows, pitch;
+  int32_t F;
+  gs_segment seg;
+  int32_t include_self;
+  gs_gemm_part p[2];
+  int32_t n_parts, combine;
+  const float* bias;
+  int32_t act, l2norm;
+  float* out;
+  int64_t ldo;
+  uint64_t* counter_dev;
+  uint64_t counter_inc;
+};
+
+__device__ __forceinline__ int64_t ls_clamp(int64_t id, int64_t n) { return (id < 0 || id >= n) ? n - 1 : id; }
+
+__global__ void __launch_bounds__(LS_THREADS) sage_layer_small_kernel(const __grid_constant__ LsParams prm) {
+  extern __shared__ float sm[];                 // xs[LS_ROWS][F] | xm[LS_ROWS][F] | red[LS_ROWS][8]
+  const int F = prm.F;
+  float* xs = sm;
+  float* xm = sm + LS_ROWS * F;
+  float* red = xm + LS_ROWS * F;
+  const gs_segment& sg = prm.seg;
+  const int k = sg.k;
+  const int64_t row0 = (int64_t)blockIdx.x * LS_ROWS;
+  // ---- phase 1: self rows and fanout means into shared memory
+  for (int idx = threadIdx.x; idx < LS_ROWS * F; idx += LS_THREADS) {
+    const int r = idx / F, c = idx - r * F;
+    const int64_t i = row0 + r;
+    float sv = 0.f, acc = 0.f;
+    if (i < sg.n) {
+      const int64_t srow = ls_clamp(sg.self_ids ? (int64_t)sg.self_ids[i] : sg.self_row0 + i, prm.n_src_rows);
+      sv = prm.src[srow * prm.pitch + c];
+      for (int j = 0; j < k; ++j) {
+        const int64_t nr = ls_clamp(sg.neigh_ids ? (int64_t)sg.neigh_ids[i * k + j] : sg.neigh_row0 + i * k + j, prm.n_src_rows);
+        acc += prm.src[nr * prm.pitch + c];
+      }
+      if (prm.include_self) acc += sv;
+      acc /= (float)(k + (prm.include_self ? 1 : 0));
+    }
+    xs[idx] = sv;
+    xm[idx] = acc;
+  }
+  __syncthreads();
+  // ---- phase 2: output columns.  CONCAT: columns [0, N0) use (xs, B0), [N0, N0+N1) use (xm, B1);
+  //               ADD: every column sums both; single part: (xm, B0).
+  const int N0 = prm.p[0].N;
+  const int ntot = (prm.n_parts == 2 && prm.combine == GS_COMBINE_CONCAT) ? N0 + prm.p[1].N : N0;
+  float ss[LS_ROWS];
+#pragma unroll
+  for (int r = 0; r < LS_ROWS; ++r) ss[r] = 0.f;
+  for (int col = threadIdx.x; col < ntot; col += LS_THREADS) {
+    float acc[LS_ROWS];
+#pragma unroll
+    for (int r = 0; r < LS_ROWS; ++r) acc[r] = 0.f;
+    for (int pi = 0; pi < prm.n_parts; ++pi) {
+      int c = col;
+      if (prm.n_parts == 2 && prm.combine == GS_COMBINE_CONCAT) {
+        if ((pi == 0) != (col < N0)) continue;
+        if (pi == 1) c = col - N0;
+      }
+      const gs_gemm_part& P = prm.p[pi];
+      const float* x = (prm.n_parts == 1 || pi == 1) ? xm : xs;
+      const float* w = P.B + c;
+      int kk = 0;
+      for (; kk + 8 <= P.K; kk += 8) {
+        float wv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + (int64_t)(kk + u) * P.ldb);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int r = 0; r < LS_ROWS; ++r) acc[r] = fmaf(x[r * F + kk + u], wv[u], acc[r]);
+      }
+      for (; kk < P.K; ++kk) {
+        const float wv = __ldg(w + (int64_t)kk * P.ldb);
+#pragma unroll
+        for (int r = 0; r < LS_ROWS; ++r) acc[r] = fmaf(x[r * F + kk], wv, acc[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < LS_ROWS; ++r) {
+      float v = acc[r];
+      if (prm.bias) v += prm.bias[col];
+      if (prm.act == GS_ACT_RELU) v = fmaxf(v, 0.f);
+      acc[r] = v;
+      ss[r] += v * v;
+    }
+#pragma unroll
+    for (int r = 0; r < LS_ROWS; ++r)
+      if (row0 + r < sg.n) prm.out[(sg.out_row0 + row0 + r) * prm.ldo + col] = acc[r];
+  }
+  // ---- phase 3: row l2-normalise (CTA-local: this CTA wrote every column of its rows)
+  if (prm.l2norm) {
+#pragma unroll
+    for (int r = 0; r < LS_ROWS; ++r) {
+      float t = ss[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if ((threadIdx.x & 31) == 0) red[r * 8 + (threadIdx.x >> 5)] = t;
+    }
+    __syncthreads();
+    float inv[LS_ROWS];
+#pragma unroll
+    for (int r = 0; r < LS_ROWS; ++r) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < LS_THREADS / 32; ++w) tot += red[r * 8 + w];
+      inv[r] = 1.0f / sqrtf(fmaxf(tot, 1e-12f));
+    }
+    for (int col = threadIdx.x; col < ntot; col += LS_THREADS) {
+#pragma unroll
+      for (int r = 0; r < LS_ROWS; ++r) {
+        if (row0 + r >= sg.n) continue;
+        float* o = prm.out + (sg.out_row0 + row0 + r) * prm.ldo + col;   // written by this same thread above
+        *o = *o * inv[r];
+      }
+    }
+  }
+  if (prm.counter_dev != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *prm.counter_dev += prm.counter_inc;
+}
+
+}  // namespace gs
+
+extern "C" int32_t gs_sage_layer_small(const float* src, int64_t n_src_rows, int32_t F, int64_t pitch,
+                                       const gs_segment* segment_host, int32_t include_self,
+                                       const gs_gemm_part* parts_host, int32_t n_parts, int32_t combine, const float* bias,
+                                       int32_t act, int32_t l2_normalize, float* out, int64_t ldo, uint64_t* counter_dev,
+                                       uint64_t counter_inc, void* stream) {
+  GS_REQUIRE(src && segment_host && parts_host && out, "gs_sage_layer_small: NULL pointer");
+  GS_REQUIRE(n_parts == 1 || n_parts == 2, "gs_sage_layer_small: n_parts=%d", n_parts);
+  GS_REQUIRE(F >= 1 && F <= 2048 && pitch >= F && n_src_rows > 0, "gs_sage_layer_small: F=%d (max 2048) / pitch", F);
+  GS_REQUIRE(segment_host->k >= 1 && segment_host->n >= 0, "gs_sage_layer_small: bad segment");
+  GS_REQUIRE(combine == GS_COMBINE_ADD || combine == GS_COMBINE_CONCAT, "gs_sage_layer_small: combine=%d", combine);
+  GS_REQUIRE(act == GS_ACT_NONE || act == GS_ACT_RELU, "gs_sage_layer_small: act=%d", act);
+  gs::LsParams prm;
+  memset(&prm, 0, sizeof(prm));
+  int ntot = 0;
+  for (int i = 0; i < n_parts; ++i) {
+    GS_REQUIRE(parts_host[i].B && parts_host[i].K == F && parts_host[i].N >= 1 && parts_host[i].ldb >= parts_host[i].N,
+               "gs_sage_layer_small: part %d must have K == F (%d) and a valid B", i, F);
+    prm.p[i] = parts_host[i];
+  }
+  if (n_parts == 2 && combine == GS_COMBINE_ADD)
+    GS_REQUIRE(parts_host[0].N == parts_host[1].N, "gs_sage_layer_small: ADD needs equal N");
+  ntot = parts_host[0].N + ((n_parts == 2 && combine == GS_COMBINE_CONCAT) ? parts_host[1].N : 0);
+  GS_REQUIRE(ntot <= 1024 && ldo >= ntot, "gs_sage_layer_small: output width %d (max 1024) / ldo", ntot);
+  if (segment_host->n == 0) return GS_OK;
+  prm.src = src; prm.n_src_rows = n_src_rows; prm.pitch = pitch; prm.F = F;
+  prm.seg = *segment_host; prm.include_self = include_self;
+  prm.n_parts = n_parts; prm.combine = combine; prm.bias = bias; prm.act = act; prm.l2norm = l2_normalize;
+  prm.out = out; prm.ldo = ldo; prm.counter_dev = counter_dev; prm.counter_inc = counter_inc;
+  const size_t smem = (size_t)(2 * gs::LS_ROWS * F + gs::LS_ROWS * 8) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GS_CUDA(cudaFuncSetAttribute(gs::sage_layer_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    attr_set = true;
+  }
+  unsigned blocks = (unsigned)((segment_host->n + gs::LS_ROWS - 1) / gs::LS_ROWS);
+  gs::sage_layer_small_kernel<<<blocks, gs::LS_THREADS, smem, (cudaStream_t)stream>>>(prm);
+  return gs::launch_check("sage_layer_small_kernel");
+}

@@ -51,6 +51,67 @@ __global__ void __launch_bounds__(256) sample_padded_kernel(const int32_t* __res
   }
 }
 
+// The whole frontier expansion (models.py:254-275) in one launch.  Warp t of each block builds hop
+// t's permutation prefix; every output element re-walks its ancestor chain from the seed
+// (hop-t element = t dependent 4-byte loads; siblings share all but the last, served by L1).
+struct KhopParams {
+  int32_t* out[GS_MAX_HOPS];
+  int32_t fanout[GS_MAX_HOPS];
+  int64_t count[GS_MAX_HOPS];     // elements of hop t+1 = n_seeds * prod(fanout[0..t])
+  int32_t n_hops;
+};
+
+__global__ void __launch_bounds__(256) sample_padded_khop_kernel(const int32_t* __restrict__ adj, int64_t n_rows,
+                                                                 int32_t max_deg, const int32_t* __restrict__ seeds,
+                                                                 const __grid_constant__ KhopParams kp, uint64_t seed,
+                                                                 uint64_t counter,
+                                                                 const uint64_t* __restrict__ counter_dev) {
+  __shared__ int16_t perm[GS_MAX_HOPS][kMaxDegSmem];
+  __shared__ int32_t pi[GS_MAX_HOPS][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < kp.n_hops) {
+    for (int j = lane; j < max_deg; j += 32) perm[warp][j] = (int16_t)j;
+    __syncwarp();
+    if (lane == 0) {
+      const uint64_t ctr = counter + (counter_dev ? *counter_dev : 0ull) + (uint64_t)warp;
+      const int k = kp.fanout[warp];
+      u32x4 r{0, 0, 0, 0};
+      for (int i = 0; i < k; ++i) {
+        if ((i & 3) == 0) {
+          u32x4 c{(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, kStreamPadded + (uint32_t)(i >> 2)};
+          r = philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        }
+        int j = i + (int)mulhi32(pick(r, i & 3), (uint32_t)(max_deg - i));
+        int16_t t = perm[warp][i];
+        perm[warp][i] = perm[warp][j];
+        perm[warp][j] = t;
+        pi[warp][i] = perm[warp][i];
+      }
+    }
+  }
+  __syncthreads();
+  int64_t total = 0;
+  for (int t = 0; t < kp.n_hops; ++t) total += kp.count[t];
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int hop = 0;
+    int64_t local = e;
+    while (local >= kp.count[hop]) { local -= kp.count[hop]; ++hop; }
+    // support size of this hop and the ancestor chain
+    int64_t sup = 1;
+    for (int t = 0; t <= hop; ++t) sup *= kp.fanout[t];
+    int64_t id = seeds[local / sup];
+    int64_t rem = local % sup;
+    for (int t = 0; t <= hop; ++t) {
+      sup /= kp.fanout[t];
+      const int j = (int)(rem / sup);
+      rem -= (int64_t)j * sup;
+      if (id < 0 || id >= n_rows) id = n_rows - 1;
+      id = adj[id * max_deg + pi[t][j]];
+    }
+    kp.out[hop][local] = (int32_t)id;
+  }
+}
+
 // One warp per requested node; lane j owns draw j (k <= 32).
 __global__ void __launch_bounds__(256) sample_csr_kernel(const int64_t* __restrict__ indptr,
                                                          const int32_t* __restrict__ indices, int64_t n_nodes,
@@ -114,6 +175,38 @@ int32_t gs_sample_padded(const int32_t* adj, int64_t n_rows, int32_t max_deg, co
   gs::sample_padded_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(adj, n_rows, max_deg, ids, n, k, col_perm,
                                                                                seed, counter, counter_dev, out);
   return gs::launch_check("sample_padded_kernel");
+}
+
+int32_t gs_sample_padded_khop(const int32_t* adj, int64_t n_rows, int32_t max_deg, const int32_t* seeds, int64_t n_seeds,
+                              const int32_t* fanout_host, int32_t n_hops, uint64_t seed, uint64_t counter,
+                              const uint64_t* counter_dev, int32_t* const* out_host, void* stream) {
+  GS_REQUIRE(n_hops >= 1 && n_hops <= GS_MAX_HOPS, "gs_sample_padded_khop: n_hops=%d (max %d)", n_hops, GS_MAX_HOPS);
+  GS_REQUIRE(fanout_host && out_host, "gs_sample_padded_khop: NULL host array");
+  GS_REQUIRE(n_seeds >= 0, "gs_sample_padded_khop: n_seeds < 0");
+  if (n_seeds == 0) return GS_OK;
+  GS_REQUIRE(adj && seeds, "gs_sample_padded_khop: NULL pointer");
+  GS_REQUIRE(n_rows > 0 && max_deg > 0 && max_deg <= gs::kMaxDegSmem, "gs_sample_padded_khop: need 0 < max_deg <= %d",
+             gs::kMaxDegSmem);
+  gs::KhopParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.n_hops = n_hops;
+  int64_t cnt = n_seeds, total = 0;
+  for (int t = 0; t < n_hops; ++t) {
+    GS_REQUIRE(fanout_host[t] >= 1 && fanout_host[t] <= max_deg && fanout_host[t] <= 64,
+               "gs_sample_padded_khop: fanout[%d]=%d (need 1..min(64, max_degree))", t, fanout_host[t]);
+    GS_REQUIRE(out_host[t] != nullptr, "gs_sample_padded_khop: out[%d] is NULL", t);
+    cnt *= fanout_host[t];
+    kp.fanout[t] = fanout_host[t];
+    kp.count[t] = cnt;
+    kp.out[t] = out_host[t];
+    total += cnt;
+  }
+  int64_t blocks = (total + 255) / 256;
+  int64_t cap = (int64_t)gs::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  gs::sample_padded_khop_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(adj, n_rows, max_deg, seeds, kp, seed,
+                                                                                    counter, counter_dev);
+  return gs::launch_check("sample_padded_khop_kernel");
 }
 
 int32_t gs_sample_csr(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, const int32_t* ids, int64_t n,

@@ -83,6 +83,8 @@ class Dense(Layer):
         if self.dropout:
             x = torch.nn.functional.dropout(x, p=float(self.dropout), training=True)
         code, post = act_code(self.act)
+        if getattr(self, "_packed", None) is None:
+            self._packed = ops.PackedWeights()
         y = ops.sage_gemm([(x, self.input_dim, self.vars["weights"])], bias=self.vars.get("bias"), act=code,
-                          math=self.math)
+                          math=self.math, packed=self._packed)
         return post(y) if post else y

@@ -87,6 +87,16 @@ class SampleAndAggregate(object):
         samples = [inputs.reshape(-1)]
         support_size = 1
         support_sizes = [support_size]
+        L = len(layer_infos)
+        fan = [layer_infos[L - k - 1].num_samples for k in range(L)]          # hop order (models.py:268-272)
+        s0 = layer_infos[0].neigh_sampler
+        if (L <= 4 and hasattr(s0, "sample_khop") and all(i.neigh_sampler is s0 for i in layer_infos)
+                and max(fan) <= 64 and samples[0].numel() == batch_size):
+            for k, ids in enumerate(s0.sample_khop(samples[0], fan)):          # one launch for all hops
+                support_size *= fan[k]
+                samples.append(ids)
+                support_sizes.append(support_size)
+            return samples, support_sizes
         for k in range(len(layer_infos)):
             t = len(layer_infos) - k - 1
             support_size *= layer_infos[t].num_samples
@@ -98,7 +108,7 @@ class SampleAndAggregate(object):
 
     # ------------------------------------------------------------------ models.py:278-330
     def aggregate(self, samples, input_features, dims, num_samples, support_sizes, batch_size=None,
-                  aggregators=None, name=None, concat=False, model_size="small"):
+                  aggregators=None, name=None, concat=False, model_size="small", _final=None):
         """At each layer, aggregate hidden representations of neighbours to compute the hidden
         representations at the next layer.  `input_features` is the feature table [N+1, F] (the
         reference passes `[self.features]` - a 1-element list - and indexes it implicitly; both forms
@@ -136,7 +146,7 @@ class SampleAndAggregate(object):
                 else:
                     segs.append(ops.Seg(counts[hop], k, self_row0=row0[hop], neigh_row0=row0[hop + 1],
                                         out_row0=row0[hop]))
-            src = aggregators[layer].aggregate_rows(src, segs)
+            src = aggregators[layer].aggregate_rows(src, segs, final=_final if layer == L - 1 else None)
         return src[:counts[0]], aggregators
 
     def _aggregate_materialised(self, samples, feats, dims, num_samples, support_sizes, batch_size, aggregators,
@@ -164,11 +174,14 @@ class SampleAndAggregate(object):
         n = batch.numel()
         samples, support = self.sample(batch, self.layer_infos, batch_size=n)
         num_samples = [info.num_samples for info in self.layer_infos]
+        final = {"l2_normalize": bool(normalize), "bump": getattr(self, "_graph_bump", None)}
         out, self.aggregators = self.aggregate(samples, [self.features], self.dims, num_samples, support,
                                                batch_size=n, aggregators=self.aggregators, concat=self.concat,
-                                               model_size=self.model_size)
-        if normalize:
+                                               model_size=self.model_size, _final=final)
+        if normalize and not final.get("normalized"):
             out = ops.l2_normalize_rows_(out.contiguous())
+        if final["bump"] is not None and not final.get("bumped"):
+            final["bump"][0].add_(final["bump"][1])
         return out
 
 
@@ -220,8 +233,11 @@ class GraphedForward(object):
             ops.STAGE_HOOK = hook
             try:
                 launches0 = ops.LAUNCHES
-                self.out = model.forward(self.ids, normalize)
-                self.counter.add_(self.n_calls)
+                model._graph_bump = (self.counter, self.n_calls)   # the step advances the device RNG counter itself
+                try:
+                    self.out = model.forward(self.ids, normalize)
+                finally:
+                    model._graph_bump = None
                 self.launches_per_replay = ops.LAUNCHES - launches0
             finally:
                 ops.STAGE_HOOK = None

@@ -36,6 +36,14 @@ class UniformNeighborSampler(Layer):
         self.counter += 1
         return out
 
+    def sample_khop(self, ids, fanouts):
+        """All hops of SampleAndAggregate.sample (reference models.py:254-275) in one kernel launch;
+        identical to len(fanouts) successive calls.  fanouts in hop order, e.g. [10, 25]."""
+        outs = ops.sample_padded_khop(self.adj_info, ids, [int(k) for k in fanouts], self.seed, self.counter,
+                                      counter_dev=self.counter_dev)
+        self.counter += len(fanouts)
+        return outs
+
 
 class CSRNeighborSampler(Layer):
     """Per-node uniform draws from a CSR adjacency (north_star's warp-per-node mode; the reference

@@ -65,6 +65,26 @@ def sample_padded(adj, ids, k, seed, counter, col_perm=None, counter_dev=None, o
     return out
 
 
+def sample_padded_khop(adj, seeds, fanouts, seed, counter, counter_dev=None):
+    """SampleAndAggregate.sample's whole frontier expansion (reference models.py:254-275) in one launch.
+    fanouts in HOP order ([10, 25]); returns [hop1 ids, hop2 ids, ...] (flat int32), bit-identical to successive
+    sample_padded calls with counters counter, counter+1, ..."""
+    require_cuda(adj, seeds, counter_dev)
+    adj, seeds = _i32(adj, "adj"), _i32(seeds.reshape(-1), "seeds")
+    n = seeds.numel()
+    outs, cnt = [], n
+    for k in fanouts:
+        cnt *= int(k)
+        outs.append(torch.empty((cnt,), dtype=torch.int32, device=adj.device))
+    fan = (_lib.c_i32 * len(fanouts))(*[int(k) for k in fanouts])
+    optr = (_lib.c_vp * len(fanouts))(*[ptr(o) for o in outs])
+    ev = _probe("sample_padded_khop")
+    check(lib().gs_sample_padded_khop(ptr(adj), adj.shape[0], adj.shape[1], ptr(seeds), n, fan, len(fanouts),
+                                      seed & _U64, counter & _U64, ptr(counter_dev), optr, stream_ptr()))
+    _launched(1 if n else 0, ev)
+    return outs
+
+
 def sample_csr(indptr, indices, ids, k, seed, counter, replace_if_short=True, pad_id=-1, counter_dev=None):
     require_cuda(indptr, indices, ids)
     if indptr.dtype != torch.int64:
@@ -189,34 +209,91 @@ def segment_max(x, n, k):
     return out
 
 
-def sage_gemm(parts, combine=COMBINE_ADD, bias=None, act=ACT_NONE, math=MATH_FP32_SIMT, out=None):
-    """parts: [(A[M, >=K] (row stride used as lda), K, B[K, N])] (1 or 2).  act(concat_or_add(A_p[:, :K] @ B_p) + bias)."""
-    M = parts[0][0].shape[0]
+def _gemm_parts(parts):
+    M = parts[0][0].shape[0] if parts[0][0] is not None else 0
     arr = (GemmPart * len(parts))()
     keep = []
     for i, (A, K, B) in enumerate(parts):
         require_cuda(A, B)
-        if A.dtype != torch.float32 or B.dtype != torch.float32:
+        if (A is not None and A.dtype != torch.float32) or B.dtype != torch.float32:
             raise TypeError("sage_gemm operands must be float32")
-        if A.stride(1) != 1 or A.shape[0] != M or A.shape[1] < K:
+        if A is not None and (A.stride(1) != 1 or A.shape[0] != M or A.shape[1] < K):
             raise ValueError("bad A operand for part %d" % i)
         B = B.contiguous()
         if B.shape[0] != K:
             raise ValueError("part %d: B has %d rows, expected K=%d" % (i, B.shape[0], K))
         keep.append(B)
-        arr[i] = GemmPart(ptr(A), A.stride(0), K, ptr(B), B.stride(0), B.shape[1])
+        arr[i] = GemmPart(ptr(A), A.stride(0) if A is not None else K, K, ptr(B), B.stride(0), B.shape[1])
+    return M, arr, keep
+
+
+class PackedWeights(object):
+    """Tensor-core weight images cached across calls (inference: the weights do not change between steps).
+    Re-packed automatically when a weight tensor is replaced or modified in place."""
+
+    def __init__(self):
+        self.key, self.ws = None, None
+
+    def get(self, parts, arr, math, dev):
+        key = (math,) + tuple((p[2].data_ptr(), p[2]._version, tuple(p[2].shape)) for p in parts)
+        if key != self.key:
+            nbytes = lib().gs_sage_gemm_workspace_bytes(1, arr, len(parts), math)
+            if nbytes < 0:
+                check(-1)
+            if self.ws is None or self.ws.numel() < nbytes:
+                self.ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=dev)
+            check(lib().gs_sage_gemm_pack(arr, len(parts), math, ptr(self.ws), stream_ptr()))
+            _launched(1)
+            self.key = key
+        return self.ws
+
+
+def sage_gemm(parts, combine=COMBINE_ADD, bias=None, act=ACT_NONE, math=MATH_FP32_SIMT, out=None, packed=None):
+    """parts: [(A[M, >=K] (row stride used as lda), K, B[K, N])] (1 or 2).  act(concat_or_add(A_p[:, :K] @ B_p) + bias).
+    packed: optional PackedWeights cache (tensor-core modes) so the weight images are built once, not per call."""
+    M, arr, keep = _gemm_parts(parts)
     ntot = sum(p[2].shape[1] for p in parts) if (combine == COMBINE_CONCAT) else parts[0][2].shape[1]
     dev = parts[0][0].device
     if out is None:
         out = torch.empty((M, ntot), dtype=torch.float32, device=dev)
-    ws_bytes = lib().gs_sage_gemm_workspace_bytes(M, arr, len(parts), math)
-    if ws_bytes < 0:
-        check(-1)
-    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes > 0 else None
+    if math == MATH_FP32_SIMT or packed is None:
+        ws_bytes = lib().gs_sage_gemm_workspace_bytes(M, arr, len(parts), math)
+        if ws_bytes < 0:
+            check(-1)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes > 0 else None
+        ev = _probe("sage_gemm/%d" % M)
+        check(lib().gs_sage_gemm(M, arr, len(parts), combine, ptr(bias), act, math, ptr(out), out.stride(0), ptr(ws),
+                                 stream_ptr()))
+        _launched((2 if ws is not None else 1) if M else 0, ev)
+        return out
+    ws = packed.get(parts, arr, math, dev)
     ev = _probe("sage_gemm/%d" % M)
-    check(lib().gs_sage_gemm(M, arr, len(parts), combine, ptr(bias), act, math, ptr(out), out.stride(0), ptr(ws),
-                             stream_ptr()))
+    check(lib().gs_sage_gemm_prepacked(M, arr, len(parts), combine, ptr(bias), act, math, ptr(out), out.stride(0),
+                                       ptr(ws), stream_ptr()))
     _launched(1 if M else 0, ev)
+    return out
+
+
+SMALL_LAYER_MAX_ROWS = 2048
+
+
+def sage_layer_small(src, seg, parts, combine=COMBINE_ADD, include_self=False, bias=None, act=ACT_NONE,
+                     l2_normalize=False, counter_dev=None, counter_inc=0):
+    """One whole aggregator layer (fanout mean -> matmuls -> add|concat -> bias -> act -> optional row
+    l2-normalise) for a small number of rows in ONE launch, exact fp32.  parts: [(None, K, B)] with K == src width."""
+    require_cuda(src, bias, counter_dev)
+    if src.dtype != torch.float32 or src.stride(1) != 1:
+        raise ValueError("src must be row-major float32")
+    _, arr, keep = _gemm_parts([(None, K, B) for (_, K, B) in parts])
+    ntot = sum(p[2].shape[1] for p in parts) if (combine == COMBINE_CONCAT) else parts[0][2].shape[1]
+    rows = seg.out_row0 + seg.n
+    out = torch.empty((rows, ntot), dtype=torch.float32, device=src.device)
+    cseg = seg.c_struct()
+    ev = _probe("sage_layer_small/%d" % rows)
+    check(lib().gs_sage_layer_small(ptr(src), src.shape[0], src.shape[1], src.stride(0), cseg, int(bool(include_self)),
+                                    arr, len(parts), combine, ptr(bias), act, int(bool(l2_normalize)), ptr(out),
+                                    out.stride(0), ptr(counter_dev), int(counter_inc), stream_ptr()))
+    _launched(1 if seg.n else 0, ev)
     return out
 
 

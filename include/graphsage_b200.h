@@ -67,6 +67,17 @@ int32_t gs_sample_padded(const int32_t* adj, int64_t n_rows, int32_t max_deg,
                          const int32_t* col_perm, uint64_t seed, uint64_t counter,
                          const uint64_t* counter_dev, int32_t* out, void* stream);
 
+/* SampleAndAggregate.sample - the whole frontier expansion (reference graphsage/models.py:254-275) in
+ * ONE launch: hop t (t = 1..n_hops) is sample_padded(samples[t-1], fanout[t-1]) with RNG counter
+ * counter + t - 1 (fanout[] is in HOP order, i.e. reversed layer order: {10, 25} for samples_1=25,
+ * samples_2=10).  out[t-1] receives the B*fanout[0]*...*fanout[t-1] ids of hop t (row-major nested).
+ * Bit-identical to n_hops successive gs_sample_padded calls.  n_hops <= GS_MAX_HOPS. */
+#define GS_MAX_HOPS 4
+int32_t gs_sample_padded_khop(const int32_t* adj, int64_t n_rows, int32_t max_deg,
+                              const int32_t* seeds, int64_t n_seeds, const int32_t* fanout_host,
+                              int32_t n_hops, uint64_t seed, uint64_t counter,
+                              const uint64_t* counter_dev, int32_t* const* out_host, void* stream);
+
 /* Per-node draws from a CSR adjacency (north_star's warp-per-node mode; no reference
  * counterpart).  Semantics: oracle/sampler.py:sample_csr.  k <= 32. */
 int32_t gs_sample_csr(const int64_t* indptr, const int32_t* indices, int64_t n_nodes,
@@ -173,6 +184,34 @@ int64_t gs_sage_gemm_workspace_bytes(int64_t M, const gs_gemm_part* parts_host, 
 int32_t gs_sage_gemm(int64_t M, const gs_gemm_part* parts_host, int32_t n_parts, int32_t combine,
                      const float* bias, int32_t act, int32_t math, float* out, int64_t ldo,
                      void* workspace, void* stream);
+
+/* Weight packing for the tensor-core modes can be hoisted out of the step when the weights do not
+ * change (inference): gs_sage_gemm_pack fills `workspace` (gs_sage_gemm_workspace_bytes) from the parts'
+ * B matrices; gs_sage_gemm_prepacked then runs only the GEMM.  gs_sage_gemm == pack + prepacked. */
+int32_t gs_sage_gemm_pack(const gs_gemm_part* parts_host, int32_t n_parts, int32_t math, void* workspace,
+                          void* stream);
+int32_t gs_sage_gemm_prepacked(int64_t M, const gs_gemm_part* parts_host, int32_t n_parts, int32_t combine,
+                               const float* bias, int32_t act, int32_t math, float* out, int64_t ldo,
+                               const void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * One whole aggregator layer for a SMALL number of output rows (the last layers of the recursion:
+ * 512 rows at batch 512) in one launch, exact fp32 FFMA:
+ *   mean over the fanout (gs_gather_mean semantics, one segment) -> two (or one) matmuls ->
+ *   add | concat -> + bias -> act -> optional row l2_normalize (reference aggregators.py:43-64 /
+ *   101-116, models.py:368).  parts: part 0 multiplies the SELF rows, part 1 the MEAN rows; with
+ *   n_parts == 1 the single part multiplies the mean rows (GCN form, include_self = 1).
+ *   parts[i].A is ignored (the operands are produced in shared memory).
+ *   If counter_dev != NULL, *counter_dev += counter_inc after the layer (advances the samplers'
+ *   device-side call counter for the next CUDA-graph replay).
+ * Limits: K_p <= 2048, total output width <= 1024.
+ * --------------------------------------------------------------------------------------------- */
+int32_t gs_sage_layer_small(const float* src, int64_t n_src_rows, int32_t F, int64_t pitch,
+                            const gs_segment* segment_host, int32_t include_self,
+                            const gs_gemm_part* parts_host, int32_t n_parts, int32_t combine,
+                            const float* bias, int32_t act, int32_t l2_normalize,
+                            float* out, int64_t ldo, uint64_t* counter_dev, uint64_t counter_inc,
+                            void* stream);
 
 /* tf.nn.l2_normalize(x, 1)   reference graphsage/models.py:368-370, supervised_models.py:85 */
 int32_t gs_l2_normalize_rows(float* x, int64_t n, int32_t C, int64_t ldx, void* stream);

@@ -382,3 +382,75 @@ def test_sage_gemm_math_modes(gs, math, shape):
     torch.cuda.synchronize()
     assert tuple(out.shape) == (M, ntot)
     assert rel_err(out.cpu().numpy(), ref) < GEMM_TOL[math], (math, shape)
+
+
+# ---------------------------------------------------------------- fused step kernels
+def test_khop_sampler_equals_successive_calls(gs):
+    rs = np.random.RandomState(8)
+    n, md = 5000, 128
+    adj = rs.randint(0, n, size=(n + 1, md)).astype(np.int32)
+    adj[n] = n
+    seeds = rs.randint(0, n + 1, size=512).astype(np.int32)
+    for fan in ([10, 25], [3], [4, 3, 2], [64, 2]):
+        outs = gs.ops.sample_padded_khop(dev(adj), dev(seeds), fan, 123, 7)
+        cur, cnt = seeds, 7
+        for k, o in zip(fan, outs):
+            cur = oracle.sample_padded(adj, cur, k, 123, cnt).reshape(-1)
+            np.testing.assert_array_equal(o.cpu().numpy(), cur)
+            cnt += 1
+    cdev = torch.tensor([5], dtype=torch.int64).cuda()
+    outs = gs.ops.sample_padded_khop(dev(adj), dev(seeds), [10, 25], 123, 2, counter_dev=cdev)
+    np.testing.assert_array_equal(outs[0].cpu().numpy(), oracle.sample_padded(adj, seeds, 10, 123, 7).reshape(-1))
+    with pytest.raises(RuntimeError, match="fanout"):
+        gs.ops.sample_padded_khop(dev(adj), dev(seeds), [65], 1, 1)
+
+
+@pytest.mark.parametrize("kind", ["mean_concat", "mean_add", "gcn"])
+def test_small_layer_matches_generic_path(gs, kind):
+    rs = np.random.RandomState(12)
+    B, k, F, D = 301, 10, 256, 128
+    H = dev(rs.randn(B + B * k, F).astype(np.float32))
+    seg = [gs.ops.Seg(B, k, self_row0=0, neigh_row0=B)]
+    bias = dev(rs.randn(2 * D if kind == "mean_concat" else D).astype(np.float32))
+    if kind == "gcn":
+        agg = gs.GCNAggregator(F, D, bias=True)
+    else:
+        agg = gs.MeanAggregator(F, D, concat=(kind == "mean_concat"), bias=True)
+    agg.vars["bias"] = bias
+    final = {"l2_normalize": True, "bump": (torch.zeros(1, dtype=torch.int64).cuda(), 3)}
+    fused = agg.aggregate_rows(H, seg, final=final)
+    assert final["normalized"] and final["bumped"] and int(final["bump"][0].item()) == 3
+    old = gs.ops.SMALL_LAYER_MAX_ROWS
+    gs.ops.SMALL_LAYER_MAX_ROWS = 0
+    try:
+        generic = gs.ops.l2_normalize_rows_(agg.aggregate_rows(H, seg).contiguous())
+    finally:
+        gs.ops.SMALL_LAYER_MAX_ROWS = old
+    assert rel_err(fused.cpu().numpy(), generic.cpu().numpy()) < 2e-6
+    # and against numpy
+    h = H.cpu().numpy()
+    selfv, neigh = h[:B], h[B:].reshape(B, k, F)
+    if kind == "gcn":
+        ref = oracle.gcn_aggregator(selfv, neigh, agg.vars["weights"].cpu().numpy(), act=lambda x: x) + bias.cpu().numpy()
+    else:
+        ref = oracle.mean_aggregator(selfv, neigh, agg.vars["neigh_weights"].cpu().numpy(),
+                                     agg.vars["self_weights"].cpu().numpy(), concat=(kind == "mean_concat"),
+                                     act=lambda x: x) + bias.cpu().numpy()
+    ref = oracle.l2_normalize(np.maximum(ref, 0))
+    assert rel_err(fused.cpu().numpy(), ref) < 1e-5
+
+
+def test_packed_weights_follow_weight_updates(gs):
+    gs.set_default_math("tf32x3")
+    try:
+        agg = gs.MeanAggregator(64, 32, concat=True)
+        x, nb = torch.randn(200, 64).cuda(), torch.randn(200, 5, 64).cuda()
+        y0 = agg((x, nb)).clone()
+        agg.vars["self_weights"].mul_(2.0)                      # in-place update must trigger a re-pack
+        y1 = agg((x, nb))
+        assert rel_err(y1[:, :32].cpu().numpy(), np.maximum(2.0 * (x @ (agg.vars["self_weights"] / 2)).cpu().numpy(), 0)) < 1e-4
+        assert torch.equal(y1[:, 32:], y0[:, 32:])
+        agg.vars["neigh_weights"] = torch.zeros_like(agg.vars["neigh_weights"])   # replacement too
+        assert float(agg((x, nb))[:, 32:].abs().max()) == 0.0
+    finally:
+        gs.set_default_math("fp32")
