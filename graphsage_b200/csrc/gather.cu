@@ -190,6 +190,122 @@ __global__ void __launch_bounds__(192) gather_mean_tma_kernel(const float* __res
 }
 
 // ------------------------------------------------------------------------------------------
+// gather + mean, TMA bulk variant 2: the rows of an output node are fetched in GROUPS of up to
+// kGroupRows rows through a two-buffer ring, so the bulk copies of group t+1 are in flight while the
+// CTA sums group t (variant 1 alternates copy and sum inside a CTA and relies on co-resident CTAs
+// for overlap).  Per-thread accumulators persist across the groups of a node.
+// ------------------------------------------------------------------------------------------
+constexpr int kGroupRows = 13;
+
+__global__ void __launch_bounds__(192) gather_mean_tma2_kernel(const float* __restrict__ src, int64_t n_src_rows, int F,
+                                                               int64_t pitch, const __grid_constant__ SegTable tab,
+                                                               int include_self, float* __restrict__ out_self,
+                                                               float* __restrict__ out_mean, int64_t out_pitch,
+                                                               int row_bytes) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar[2];
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int ncol4 = (int)(out_pitch >> 2);
+  const int row_f4 = row_bytes >> 4;
+  const size_t buf_bytes = (size_t)kGroupRows * row_bytes;
+
+  // work items of this CTA: (node r, group g); enumerate lazily
+  int64_t r_issue = blockIdx.x;      // node whose groups are being issued
+  int g_issue = 0;
+  auto issue = [&](int buf) -> bool {   // post the copies of the next (node, group) into `buf`; false if none left
+    if (r_issue >= tab.total_rows) return false;
+    int64_t i;
+    const gs_segment& sg = tab.s[find_segment(tab, r_issue, i)];
+    const int k = sg.k;
+    const int rows_total = k + 1;                         // neighbours then self
+    const int first = g_issue * kGroupRows;
+    const int cnt = min(kGroupRows, rows_total - first);
+    if (threadIdx.x < 32) {
+      if (threadIdx.x == 0) mbar_expect_tx(&bar[buf], (uint32_t)(cnt * row_bytes));
+      __syncwarp();
+      for (int j = threadIdx.x; j < cnt; j += 32) {
+        const int jj = first + j;
+        int64_t id;
+        if (jj < k) id = sg.neigh_ids ? (int64_t)sg.neigh_ids[i * k + jj] : sg.neigh_row0 + i * k + jj;
+        else id = sg.self_ids ? (int64_t)sg.self_ids[i] : sg.self_row0 + i;
+        id = clamp_row(id, n_src_rows);
+        bulk_g2s(smem + buf * buf_bytes + (size_t)j * row_bytes, src + id * pitch, (uint32_t)row_bytes, &bar[buf]);
+      }
+    }
+    if (first + cnt >= rows_total) { r_issue += gridDim.x; g_issue = 0; } else { ++g_issue; }
+    return true;
+  };
+
+  uint32_t phase[2] = {0u, 0u};
+  int buf = 0;
+  bool have = issue(0);
+  int64_t r = blockIdx.x;
+  int g = 0;
+  float4 acc[2];                                          // up to 2 float4 columns per thread (ncol4 <= 2 * blockDim)
+  acc[0] = acc[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  while (have) {
+    const bool have_next = issue(buf ^ 1);                // prefetch the next group into the other buffer
+    int64_t i;
+    const gs_segment& sg = tab.s[find_segment(tab, r, i)];
+    const int k = sg.k;
+    const int rows_total = k + 1;
+    const int first = g * kGroupRows;
+    const int cnt = min(kGroupRows, rows_total - first);
+    const bool last = first + cnt >= rows_total;
+    mbar_wait(&bar[buf], phase[buf]);
+    phase[buf] ^= 1u;
+    const float4* rows = reinterpret_cast<const float4*>(smem + buf * buf_bytes);
+    const int nn = last ? cnt - 1 : cnt;                  // neighbour rows in this group (the self row is the node's last row)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int c = threadIdx.x + q * blockDim.x;
+      if (c < ncol4 && c * 4 < F) {
+        float4 a = acc[q];
+        for (int j = 0; j < nn; ++j) {
+          float4 v = rows[j * row_f4 + c];
+          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        acc[q] = a;
+      }
+    }
+    if (last) {
+      const int64_t orow = sg.out_row0 + i;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c = threadIdx.x + q * blockDim.x;
+        if (c < ncol4) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), sv = a;
+          if (c * 4 < F) {
+            a = acc[q];
+            sv = rows[(cnt - 1) * row_f4 + c];
+            const float div = (float)(k + (include_self ? 1 : 0));
+            if (include_self) { a.x += sv.x; a.y += sv.y; a.z += sv.z; a.w += sv.w; }
+            a.x /= div; a.y /= div; a.z /= div; a.w /= div;
+            a = mask_tail(a, c * 4, F);
+            sv = mask_tail(sv, c * 4, F);
+          }
+          reinterpret_cast<float4*>(out_mean + orow * out_pitch)[c] = a;
+          if (out_self) reinterpret_cast<float4*>(out_self + orow * out_pitch)[c] = sv;
+          acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      r += gridDim.x;
+      g = 0;
+    } else {
+      ++g;
+    }
+    __syncthreads();                                       // buffer `buf` fully read before it is refilled
+    buf ^= 1;
+    have = have_next;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // plain row gather.  TMA variant: each lane of a one-warp CTA moves one row
 // global -> shared -> global entirely with the bulk-copy engine (no register traffic).
 // ------------------------------------------------------------------------------------------
@@ -434,7 +550,29 @@ int32_t gs_gather_mean(const void* src, int32_t dtype, int64_t n_src_rows, int32
   const int row_bytes = ((F + 3) / 4) * 16;
   const size_t smem = (size_t)row_bytes * (kmax + 1);
   const int variant = gs::tuning("gather_variant", 1);
-  if (variant == 1 && smem <= 200 * 1024) {
+  if (variant == 2 && ncol4 <= 2 * 160) {
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      GS_CUDA(cudaFuncSetAttribute(gs::gather_mean_tma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr2_set = true;
+    }
+    const size_t smem2 = (size_t)2 * gs::kGroupRows * row_bytes;
+    int threads = ((ncol4 + 31) / 32) * 32;
+    if (threads > 160) threads = 160;
+    if (threads < 32) threads = 32;
+    int per_sm = (int)((224 * 1024) / (smem2 + 1024));
+    if (per_sm < 1) per_sm = 1;
+    int lim = gs::tuning("gather_ctas_per_sm", 8);
+    if (per_sm > lim) per_sm = lim;
+    int64_t blocks = tab.total_rows;
+    int64_t cap = (int64_t)gs::sm_count() * per_sm;
+    if (blocks > cap) blocks = cap;
+    gs::gather_mean_tma2_kernel<<<(unsigned)blocks, threads, smem2, st>>>(fsrc, n_src_rows, F, pitch, tab, include_self,
+                                                                          (float*)out_self, (float*)out_mean, out_pitch,
+                                                                          row_bytes);
+    return gs::launch_check("gather_mean_tma2_kernel");
+  }
+  if (variant >= 1 && smem <= 200 * 1024) {
     static bool attr_set = false;
     if (!attr_set) {
       GS_CUDA(cudaFuncSetAttribute(gs::gather_mean_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -8,8 +8,8 @@
 
 namespace gs {
 
-constexpr int LS_ROWS = 4;
-constexpr int LS_THREADS = 256;
+constexpr int LS_ROWS = 8;
+constexpr int LS_THREADS = 512;
 
 struct LsParams {
   const float* src;
@@ -29,42 +29,71 @@ struct LsParams {
 
 __device__ __forceinline__ int64_t ls_clamp(int64_t id, int64_t n) { return (id < 0 || id >= n) ? n - 1 : id; }
 
+// Latency is the enemy here (one CTA per SM, a few rows each): every load batch is made of
+// independent loads (LS_ROWS rows x 5 neighbours in phase 1, 8 weight rows x K-slices in phase 2).
 __global__ void __launch_bounds__(LS_THREADS) sage_layer_small_kernel(const __grid_constant__ LsParams prm) {
-  extern __shared__ float sm[];                 // xs[LS_ROWS][F] | xm[LS_ROWS][F] | red[LS_ROWS][8]
+  extern __shared__ float sm[];     // xs[LS_ROWS][F] | xm[LS_ROWS][F] | part[nslices][LS_ROWS][ncolp] | red[LS_ROWS][16]
   const int F = prm.F;
   float* xs = sm;
   float* xm = sm + LS_ROWS * F;
-  float* red = xm + LS_ROWS * F;
   const gs_segment& sg = prm.seg;
   const int k = sg.k;
   const int64_t row0 = (int64_t)blockIdx.x * LS_ROWS;
-  // ---- phase 1: self rows and fanout means into shared memory
-  for (int idx = threadIdx.x; idx < LS_ROWS * F; idx += LS_THREADS) {
-    const int r = idx / F, c = idx - r * F;
-    const int64_t i = row0 + r;
-    float sv = 0.f, acc = 0.f;
-    if (i < sg.n) {
-      const int64_t srow = ls_clamp(sg.self_ids ? (int64_t)sg.self_ids[i] : sg.self_row0 + i, prm.n_src_rows);
-      sv = prm.src[srow * prm.pitch + c];
-      for (int j = 0; j < k; ++j) {
-        const int64_t nr = ls_clamp(sg.neigh_ids ? (int64_t)sg.neigh_ids[i * k + j] : sg.neigh_row0 + i * k + j, prm.n_src_rows);
-        acc += prm.src[nr * prm.pitch + c];
+  // ---- phase 1: self rows and fanout means into shared memory (thread = column, all rows at once)
+  for (int c = threadIdx.x; c < F; c += LS_THREADS) {
+    float acc[LS_ROWS], sv[LS_ROWS];
+#pragma unroll
+    for (int r = 0; r < LS_ROWS; ++r) {
+      acc[r] = 0.f;
+      const int64_t i = row0 + r;
+      sv[r] = 0.f;
+      if (i < sg.n) {
+        const int64_t srow = ls_clamp(sg.self_ids ? (int64_t)sg.self_ids[i] : sg.self_row0 + i, prm.n_src_rows);
+        sv[r] = prm.src[srow * prm.pitch + c];
       }
-      if (prm.include_self) acc += sv;
-      acc /= (float)(k + (prm.include_self ? 1 : 0));
     }
-    xs[idx] = sv;
-    xm[idx] = acc;
+    for (int j0 = 0; j0 < k; j0 += 5) {
+      float v[LS_ROWS][5];
+#pragma unroll
+      for (int r = 0; r < LS_ROWS; ++r) {
+        const int64_t i = row0 + r;
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+          v[r][u] = 0.f;
+          if (i < sg.n && j0 + u < k) {
+            const int64_t nr = ls_clamp(sg.neigh_ids ? (int64_t)sg.neigh_ids[i * k + j0 + u] : sg.neigh_row0 + i * k + j0 + u,
+                                        prm.n_src_rows);
+            v[r][u] = prm.src[nr * prm.pitch + c];
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < LS_ROWS; ++r)
+#pragma unroll
+        for (int u = 0; u < 5; ++u) acc[r] += v[r][u];
+    }
+#pragma unroll
+    for (int r = 0; r < LS_ROWS; ++r) {
+      float a = acc[r];
+      if (prm.include_self) a += sv[r];
+      a /= (float)(k + (prm.include_self ? 1 : 0));
+      xs[r * F + c] = sv[r];
+      xm[r * F + c] = (row0 + r < sg.n) ? a : 0.f;
+    }
   }
   __syncthreads();
-  // ---- phase 2: output columns.  CONCAT: columns [0, N0) use (xs, B0), [N0, N0+N1) use (xm, B1);
-  //               ADD: every column sums both; single part: (xm, B0).
+  // ---- phase 2: output columns, K split over `nslices` thread groups.
+  //      CONCAT: columns [0, N0) use (xs, B0), [N0, N0+N1) use (xm, B1); ADD: every column sums both parts;
+  //      single part: (xm, B0).
   const int N0 = prm.p[0].N;
   const int ntot = (prm.n_parts == 2 && prm.combine == GS_COMBINE_CONCAT) ? N0 + prm.p[1].N : N0;
-  float ss[LS_ROWS];
-#pragma unroll
-  for (int r = 0; r < LS_ROWS; ++r) ss[r] = 0.f;
-  for (int col = threadIdx.x; col < ntot; col += LS_THREADS) {
+  const int ncolp = (ntot + 31) & ~31;
+  const int nslices = ncolp <= LS_THREADS ? LS_THREADS / ncolp : 1;
+  float* part = xm + LS_ROWS * F;                       // [nslices][LS_ROWS][ncolp]
+  float* red = part + nslices * LS_ROWS * ncolp;        // [LS_ROWS][16]
+  const int slice = nslices == 1 ? 0 : threadIdx.x / ncolp;
+  const int col_step = nslices == 1 ? LS_THREADS : ncolp;
+  for (int col = (nslices == 1 ? threadIdx.x : threadIdx.x % ncolp); col < ntot && slice < nslices; col += col_step) {
     float acc[LS_ROWS];
 #pragma unroll
     for (int r = 0; r < LS_ROWS; ++r) acc[r] = 0.f;
@@ -77,8 +106,10 @@ __global__ void __launch_bounds__(LS_THREADS) sage_layer_small_kernel(const __gr
       const gs_gemm_part& P = prm.p[pi];
       const float* x = (prm.n_parts == 1 || pi == 1) ? xm : xs;
       const float* w = P.B + c;
-      int kk = 0;
-      for (; kk + 8 <= P.K; kk += 8) {
+      const int kchunk = (((P.K + nslices - 1) / nslices) + 7) & ~7;
+      const int kbeg = slice * kchunk, kend = min(P.K, kbeg + kchunk);
+      int kk = kbeg;
+      for (; kk + 8 <= kend; kk += 8) {
         float wv[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + (int64_t)(kk + u) * P.ldb);
@@ -87,50 +118,56 @@ __global__ void __launch_bounds__(LS_THREADS) sage_layer_small_kernel(const __gr
 #pragma unroll
           for (int r = 0; r < LS_ROWS; ++r) acc[r] = fmaf(x[r * F + kk + u], wv[u], acc[r]);
       }
-      for (; kk < P.K; ++kk) {
+      for (; kk < kend; ++kk) {
         const float wv = __ldg(w + (int64_t)kk * P.ldb);
 #pragma unroll
         for (int r = 0; r < LS_ROWS; ++r) acc[r] = fmaf(x[r * F + kk], wv, acc[r]);
       }
     }
 #pragma unroll
+    for (int r = 0; r < LS_ROWS; ++r) part[(slice * LS_ROWS + r) * ncolp + col] = acc[r];
+    if (nslices > 1) break;                              // one (column, slice) per thread when K is sliced
+  }
+  __syncthreads();
+  // ---- phase 3: reduce the K slices, bias, activation, row sum of squares, store
+  float ss[LS_ROWS];
+#pragma unroll
+  for (int r = 0; r < LS_ROWS; ++r) ss[r] = 0.f;
+  for (int col = threadIdx.x; col < ntot; col += LS_THREADS) {
+#pragma unroll
     for (int r = 0; r < LS_ROWS; ++r) {
-      float v = acc[r];
+      float v = 0.f;
+      for (int s2 = 0; s2 < nslices; ++s2) v += part[(s2 * LS_ROWS + r) * ncolp + col];
       if (prm.bias) v += prm.bias[col];
       if (prm.act == GS_ACT_RELU) v = fmaxf(v, 0.f);
-      acc[r] = v;
       ss[r] += v * v;
+      part[r * ncolp + col] = v;                         // slice-0 slot now holds the finished value (same thread re-reads it)
     }
-#pragma unroll
-    for (int r = 0; r < LS_ROWS; ++r)
-      if (row0 + r < sg.n) prm.out[(sg.out_row0 + row0 + r) * prm.ldo + col] = acc[r];
   }
-  // ---- phase 3: row l2-normalise (CTA-local: this CTA wrote every column of its rows)
+  float inv[LS_ROWS];
+#pragma unroll
+  for (int r = 0; r < LS_ROWS; ++r) inv[r] = 1.f;
   if (prm.l2norm) {
 #pragma unroll
     for (int r = 0; r < LS_ROWS; ++r) {
       float t = ss[r];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if ((threadIdx.x & 31) == 0) red[r * 8 + (threadIdx.x >> 5)] = t;
+      if ((threadIdx.x & 31) == 0) red[r * 16 + (threadIdx.x >> 5)] = t;
     }
     __syncthreads();
-    float inv[LS_ROWS];
 #pragma unroll
     for (int r = 0; r < LS_ROWS; ++r) {
       float tot = 0.f;
 #pragma unroll
-      for (int w = 0; w < LS_THREADS / 32; ++w) tot += red[r * 8 + w];
+      for (int w = 0; w < LS_THREADS / 32; ++w) tot += red[r * 16 + w];
       inv[r] = 1.0f / sqrtf(fmaxf(tot, 1e-12f));
     }
-    for (int col = threadIdx.x; col < ntot; col += LS_THREADS) {
+  }
+  for (int col = threadIdx.x; col < ntot; col += LS_THREADS) {
 #pragma unroll
-      for (int r = 0; r < LS_ROWS; ++r) {
-        if (row0 + r >= sg.n) continue;
-        float* o = prm.out + (sg.out_row0 + row0 + r) * prm.ldo + col;   // written by this same thread above
-        *o = *o * inv[r];
-      }
-    }
+    for (int r = 0; r < LS_ROWS; ++r)
+      if (row0 + r < sg.n) prm.out[(sg.out_row0 + row0 + r) * prm.ldo + col] = part[r * ncolp + col] * inv[r];
   }
   if (prm.counter_dev != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *prm.counter_dev += prm.counter_inc;
 }
@@ -165,10 +202,13 @@ extern "C" int32_t gs_sage_layer_small(const float* src, int64_t n_src_rows, int
   prm.seg = *segment_host; prm.include_self = include_self;
   prm.n_parts = n_parts; prm.combine = combine; prm.bias = bias; prm.act = act; prm.l2norm = l2_normalize;
   prm.out = out; prm.ldo = ldo; prm.counter_dev = counter_dev; prm.counter_inc = counter_inc;
-  const size_t smem = (size_t)(2 * gs::LS_ROWS * F + gs::LS_ROWS * 8) * sizeof(float);
+  const int ncolp = (ntot + 31) & ~31;
+  const int nslices = ncolp <= gs::LS_THREADS ? gs::LS_THREADS / ncolp : 1;
+  const size_t smem = (size_t)(2 * gs::LS_ROWS * F + nslices * gs::LS_ROWS * ncolp + gs::LS_ROWS * 16) * sizeof(float);
+  GS_REQUIRE(smem <= 200 * 1024, "gs_sage_layer_small: needs %zu bytes of shared memory", smem);
   static bool attr_set = false;
   if (!attr_set) {
-    GS_CUDA(cudaFuncSetAttribute(gs::sage_layer_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    GS_CUDA(cudaFuncSetAttribute(gs::sage_layer_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   unsigned blocks = (unsigned)((segment_host->n + gs::LS_ROWS - 1) / gs::LS_ROWS);

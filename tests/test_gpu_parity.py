@@ -118,7 +118,7 @@ def test_gather_rows_exact(gs, variant, F):
         gs._lib.set_tuning("gather_variant", 1)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_gather_mean_matches_numpy(gs, variant):
     rs = np.random.RandomState(9)
     n_src, F = 3000, 602
@@ -340,7 +340,7 @@ def test_graphed_forward_matches_eager_and_oracle(gs):
 
 
 # ---------------------------------------------------------------- tcgen05 GEMM (all math modes) vs fp64
-GEMM_TOL = {"fp32": 2e-6, "tf32x3": 5e-6, "tf32": 3e-3, "bf16": 2e-2}
+GEMM_TOL = {"fp32": 2e-6, "tf32x3": 2e-5, "tf32": 3e-3, "bf16": 2e-2}
 
 
 @pytest.mark.parametrize("math", ["fp32", "tf32x3", "tf32", "bf16"])

@@ -56,8 +56,8 @@ rows = B * 11
 gbytes = B * 261 * F * 4
 xs = torch.empty((rows, P), device=dev)
 xm = torch.empty((rows, P), device=dev)
-for variant in (1, 0):
-    for cps in (1, 2, 3, 4, 6, 8):
+for variant in (2, 1, 0):
+    for cps in (2, 3, 4, 8):
         gs._lib.set_tuning("gather_variant", variant)
         gs._lib.set_tuning("gather_ctas_per_sm", cps)
 
@@ -97,12 +97,29 @@ for math in ("fp32", "tf32x3", "tf32", "bf16"):
         print("gemm", math, "unavailable:", str(e)[:80])
 med, _ = timeit(lambda i: torch.relu(torch.cat([xs[:, :F] @ Ws, xm[:, :F] @ Wn], 1)))
 res["torch_gemm_l0"] = {"ms_median": med}
+# fused small layer (layer 1 at bench size): [512 rows] mean over 10 of [5120, 256] -> 2 x [256,128] -> l2norm
+H1 = torch.randn(B * 11, 256, device=dev)
+W1s, W1n = torch.randn(256, 128, device=dev), torch.randn(256, 128, device=dev)
+seg1 = ops.Seg(B, 10, self_row0=0, neigh_row0=B)
+med, mn = timeit(lambda i: ops.sage_layer_small(H1, seg1, [(None, 256, W1s), (None, 256, W1n)], combine=ops.COMBINE_CONCAT,
+                                                l2_normalize=True))
+res["layer_small_512"] = {"ms_median": med, "ms_min": mn}
+print("layer_small", med, flush=True)
+packed = ops.PackedWeights()
+for math in ("tf32x3", "bf16"):
+    code = gs.aggregators._MATH_NAMES[math]
+    med, mn = timeit(lambda i: ops.sage_gemm([(xs, F, Ws), (xm, F, Wn)], combine=ops.COMBINE_CONCAT, act=ops.ACT_RELU,
+                                             math=code, packed=packed))
+    res["gemm_l0_prepacked_" + math] = {"ms_median": med, "ms_min": mn}
+    print("gemm prepacked", math, med, flush=True)
 # sampler
 adj = torch.randint(0, N, (N + 1, 128), device=dev, dtype=torch.int32)
 med, _ = timeit(lambda i: ops.sample_padded(adj, sets[i][1], 25, 123, i))
 res["sample_5120x25"] = {"ms_median": med}
 med, _ = timeit(lambda i: ops.sample_padded(adj, sets[i][0], 10, 123, i))
 res["sample_512x10"] = {"ms_median": med}
+med, _ = timeit(lambda i: ops.sample_padded_khop(adj, sets[i][0], [10, 25], 123, i))
+res["sample_khop_512x10x25"] = {"ms_median": med}
 print(json.dumps(res, indent=1))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/micro_%s.json" % os.environ.get("MICRO_TAG", "r1"), "w"), indent=1)
