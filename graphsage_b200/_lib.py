@@ -83,6 +83,10 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(_lib, name)          # AttributeError = symbol not exported
             fn.restype, fn.argtypes = res, args
+        for kv in os.environ.get("GS_TUNING", "").split(","):      # e.g. GS_TUNING=gather_variant=2,gather_ctas_per_sm=3
+            if "=" in kv:
+                k, v = kv.split("=", 1)
+                _lib.gs_set_tuning(k.strip().encode(), int(v))
     return _lib
 
 

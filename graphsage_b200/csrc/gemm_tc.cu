@@ -211,36 +211,22 @@ __device__ __forceinline__ void load_a_chunk(const TcPart& P, int64_t M, int64_t
   }
 }
 
-// a fetched chunk as it is kept in the register pipeline: tf32 modes = 4 raw fp32, bf16 mode = 8 packed bf16
 template <int MODE>
-__device__ __forceinline__ uint4 pack_a_chunk(const float (&v)[8]) {
-  uint4 u;
+__device__ __forceinline__ void store_a_chunk(unsigned char* a_img, int row, int c, const float (&v)[8]) {
+  const uint32_t off = sw128_off(row, c);
   if constexpr (MODE == 2) {
     __nv_bfloat162 h[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-    u = *reinterpret_cast<uint4*>(h);
-  } else {
-    u.x = __float_as_uint(v[0]); u.y = __float_as_uint(v[1]); u.z = __float_as_uint(v[2]); u.w = __float_as_uint(v[3]);
-  }
-  return u;
-}
-
-template <int MODE>
-__device__ __forceinline__ void store_a_chunk(unsigned char* a_img, int row, int c, const uint4& u) {
-  const uint32_t off = sw128_off(row, c);
-  if constexpr (MODE == 2) {
-    *reinterpret_cast<uint4*>(a_img + off) = u;
+    *reinterpret_cast<uint4*>(a_img + off) = *reinterpret_cast<uint4*>(h);
   } else {
     uint4 hi;
-    hi.x = u.x & 0xFFFFE000u; hi.y = u.y & 0xFFFFE000u; hi.z = u.z & 0xFFFFE000u; hi.w = u.w & 0xFFFFE000u;
+    hi.x = tf32_mask(v[0]); hi.y = tf32_mask(v[1]); hi.z = tf32_mask(v[2]); hi.w = tf32_mask(v[3]);
     *reinterpret_cast<uint4*>(a_img + off) = hi;
     if constexpr (MODE == 0) {
       uint4 lo;
-      lo.x = tf32_mask(__uint_as_float(u.x) - __uint_as_float(hi.x));
-      lo.y = tf32_mask(__uint_as_float(u.y) - __uint_as_float(hi.y));
-      lo.z = tf32_mask(__uint_as_float(u.z) - __uint_as_float(hi.z));
-      lo.w = tf32_mask(__uint_as_float(u.w) - __uint_as_float(hi.w));
+      lo.x = tf32_mask(v[0] - __uint_as_float(hi.x)); lo.y = tf32_mask(v[1] - __uint_as_float(hi.y));
+      lo.z = tf32_mask(v[2] - __uint_as_float(hi.z)); lo.w = tf32_mask(v[3] - __uint_as_float(hi.w));
       *reinterpret_cast<uint4*>(a_img + TC_TILE_BYTES + off) = lo;
     }
   }
@@ -292,49 +278,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __gri
     const int group = warp >> 2;
     const int tg = threadIdx.x & 127;
     const int c = tg & 7, r0 = tg >> 3;
+    float cur[8][8];
     auto locate = [&](int it, int& pi, int& kb) {
       pi = part_lo; kb = it;
       while (kb >= prm.p[pi].kblocks) { kb -= prm.p[pi].kblocks; ++pi; }
     };
-    auto fetch = [&](int it, uint4 (&dst)[8]) {
+    auto fetch = [&](int it, float (&dst)[8][8]) {
       int pi, kb;
       locate(it, pi, kb);
       const TcPart& P = prm.p[pi];
       const bool vec = ((P.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.A) & 15u) == 0);
       const int gcol = kb * C::BK + c * (MODE == 2 ? 8 : 4);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float v[8];
-        load_a_chunk<MODE>(P, prm.M, m0 + r0 + 16 * i, gcol, vec, v);
-        dst[i] = pack_a_chunk<MODE>(v);
-      }
+      for (int i = 0; i < 8; ++i) load_a_chunk<MODE>(P, prm.M, m0 + r0 + 16 * i, gcol, vec, dst[i]);
     };
-    // Register pipeline: each group keeps TWO of its K-blocks in flight beyond the one it is converting
-    // (buffers rotate A -> B -> C), so global-load latency is covered by ~4 K-blocks per CTA.
-    auto produce = [&](int it, const uint4 (&buf)[8]) {
+    int it = group;
+    if (it < total_it) fetch(it, cur);
+    for (; it < total_it; it += 2) {
       const int s = it % C::STAGES;
       const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
+      float nxt[8][8];
+      const bool more = it + 2 < total_it;
+      if (more) fetch(it + 2, nxt);                    // prefetch this group's next K-block
       mbar_wait(&empty_bar[s], ph ^ 1u);
       unsigned char* a_img = smem + (size_t)s * C::STAGE_BYTES;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) store_a_chunk<MODE>(a_img, r0 + 16 * i, c, buf[i]);
+      for (int i = 0; i < 8; ++i) store_a_chunk<MODE>(a_img, r0 + 16 * i, c, cur[i]);
       fence_proxy_async();                             // generic-proxy stores -> visible to the MMA (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_a[s]);
-    };
-    uint4 bufA[8], bufB[8], bufC[8];
-    int it = group;
-    if (it < total_it) fetch(it, bufA);
-    if (it + 2 < total_it) fetch(it + 2, bufB);
-    for (; it < total_it; it += 6) {
-      if (it + 4 < total_it) fetch(it + 4, bufC);
-      produce(it, bufA);
-      if (it + 2 >= total_it) break;
-      if (it + 6 < total_it) fetch(it + 6, bufA);
-      produce(it + 2, bufB);
-      if (it + 4 >= total_it) break;
-      if (it + 8 < total_it) fetch(it + 8, bufB);
-      produce(it + 4, bufC);
+      if (more) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) cur[i][e] = nxt[i][e];
+      }
     }
     // =============================== epilogue ===============================
     mbar_wait(&accum_bar, 0);

@@ -25,6 +25,7 @@ struct LsParams {
   int64_t ldo;
   uint64_t* counter_dev;
   uint64_t counter_inc;
+  int32_t vec;          // everything 16-byte friendly: 128-bit loads in both phases
 };
 
 __device__ __forceinline__ int64_t ls_clamp(int64_t id, int64_t n) { return (id < 0 || id >= n) ? n - 1 : id; }
@@ -39,7 +40,39 @@ __global__ void __launch_bounds__(LS_THREADS) sage_layer_small_kernel(const __gr
   const gs_segment& sg = prm.seg;
   const int k = sg.k;
   const int64_t row0 = (int64_t)blockIdx.x * LS_ROWS;
-  // ---- phase 1: self rows and fanout means into shared memory (thread = column, all rows at once)
+  // ---- phase 1: self rows and fanout means into shared memory
+  if (prm.vec) {
+    // thread = (row, float4 column); neighbours in independent batches of 5 x 128-bit loads
+    const int f4 = F >> 2;
+    for (int p = threadIdx.x; p < f4 * LS_ROWS; p += LS_THREADS) {
+      const int r = p / f4, c4 = p - r * f4;
+      const int64_t i = row0 + r;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), sv = acc;
+      if (i < sg.n) {
+        const int64_t srow = ls_clamp(sg.self_ids ? (int64_t)sg.self_ids[i] : sg.self_row0 + i, prm.n_src_rows);
+        sv = ldg_nc_f4(reinterpret_cast<const float4*>(prm.src + srow * prm.pitch) + c4);
+        for (int j0 = 0; j0 < k; j0 += 5) {
+          float4 v[5];
+#pragma unroll
+          for (int u = 0; u < 5; ++u) {
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j0 + u < k) {
+              const int64_t nr = ls_clamp(sg.neigh_ids ? (int64_t)sg.neigh_ids[i * k + j0 + u] : sg.neigh_row0 + i * k + j0 + u,
+                                          prm.n_src_rows);
+              v[u] = ldg_nc_f4(reinterpret_cast<const float4*>(prm.src + nr * prm.pitch) + c4);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 5; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+        }
+        const float div = (float)(k + (prm.include_self ? 1 : 0));
+        if (prm.include_self) { acc.x += sv.x; acc.y += sv.y; acc.z += sv.z; acc.w += sv.w; }
+        acc.x /= div; acc.y /= div; acc.z /= div; acc.w /= div;
+      }
+      reinterpret_cast<float4*>(xs + r * F)[c4] = sv;
+      reinterpret_cast<float4*>(xm + r * F)[c4] = acc;
+    }
+  } else
   for (int c = threadIdx.x; c < F; c += LS_THREADS) {
     float acc[LS_ROWS], sv[LS_ROWS];
 #pragma unroll
@@ -88,10 +121,55 @@ __global__ void __launch_bounds__(LS_THREADS) sage_layer_small_kernel(const __gr
   const int N0 = prm.p[0].N;
   const int ntot = (prm.n_parts == 2 && prm.combine == GS_COMBINE_CONCAT) ? N0 + prm.p[1].N : N0;
   const int ncolp = (ntot + 31) & ~31;
-  const int nslices = ncolp <= LS_THREADS ? LS_THREADS / ncolp : 1;
+  const int ncgp = prm.vec ? ((((ntot + 3) >> 2) + 31) & ~31) : 0;       // padded number of 4-column groups
+  const int nslices = prm.vec ? (ncgp <= LS_THREADS ? LS_THREADS / ncgp : 1) : (ncolp <= LS_THREADS ? LS_THREADS / ncolp : 1);
   float* part = xm + LS_ROWS * F;                       // [nslices][LS_ROWS][ncolp]
   float* red = part + nslices * LS_ROWS * ncolp;        // [LS_ROWS][16]
-  const int slice = nslices == 1 ? 0 : threadIdx.x / ncolp;
+  if (prm.vec) {
+    // thread = (4-column group, K slice): per 4 k-steps 4 x LDG.128 of W rows, 8 x LDS.128 of x, 128 FMA
+    const int ncg = ntot >> 2;
+    const int sl = threadIdx.x / ncgp;
+    const int cg0 = threadIdx.x - sl * ncgp;
+    for (int cg = cg0; cg < ncg && sl < nslices; cg += (nslices == 1 ? LS_THREADS : ncgp)) {
+      const int col = cg * 4;
+      float4 acc[LS_ROWS];
+#pragma unroll
+      for (int r = 0; r < LS_ROWS; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int pi = 0; pi < prm.n_parts; ++pi) {
+        int c = col;
+        if (prm.n_parts == 2 && prm.combine == GS_COMBINE_CONCAT) {
+          if ((pi == 0) != (col < N0)) continue;
+          if (pi == 1) c = col - N0;
+        }
+        const gs_gemm_part& P = prm.p[pi];
+        const float* x = (prm.n_parts == 1 || pi == 1) ? xm : xs;
+        const float* w = P.B + c;
+        const int kchunk = (((P.K + nslices - 1) / nslices) + 3) & ~3;
+        const int kbeg = sl * kchunk, kend = min(P.K, kbeg + kchunk);   // K % 4 == 0 in the vector path
+        for (int kk = kbeg; kk < kend; kk += 4) {
+          float4 wv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) wv[u] = __ldg(reinterpret_cast<const float4*>(w + (int64_t)(kk + u) * P.ldb));
+#pragma unroll
+          for (int r = 0; r < LS_ROWS; ++r) {
+            const float4 xv = *reinterpret_cast<const float4*>(x + r * F + kk);
+            acc[r].x = fmaf(xv.x, wv[0].x, acc[r].x); acc[r].y = fmaf(xv.x, wv[0].y, acc[r].y);
+            acc[r].z = fmaf(xv.x, wv[0].z, acc[r].z); acc[r].w = fmaf(xv.x, wv[0].w, acc[r].w);
+            acc[r].x = fmaf(xv.y, wv[1].x, acc[r].x); acc[r].y = fmaf(xv.y, wv[1].y, acc[r].y);
+            acc[r].z = fmaf(xv.y, wv[1].z, acc[r].z); acc[r].w = fmaf(xv.y, wv[1].w, acc[r].w);
+            acc[r].x = fmaf(xv.z, wv[2].x, acc[r].x); acc[r].y = fmaf(xv.z, wv[2].y, acc[r].y);
+            acc[r].z = fmaf(xv.z, wv[2].z, acc[r].z); acc[r].w = fmaf(xv.z, wv[2].w, acc[r].w);
+            acc[r].x = fmaf(xv.w, wv[3].x, acc[r].x); acc[r].y = fmaf(xv.w, wv[3].y, acc[r].y);
+            acc[r].z = fmaf(xv.w, wv[3].z, acc[r].z); acc[r].w = fmaf(xv.w, wv[3].w, acc[r].w);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < LS_ROWS; ++r) *reinterpret_cast<float4*>(part + (sl * LS_ROWS + r) * ncolp + col) = acc[r];
+      if (nslices > 1) break;
+    }
+  }
+  const int slice = prm.vec ? nslices : (nslices == 1 ? 0 : threadIdx.x / ncolp);   // vec: scalar loop below is skipped
   const int col_step = nslices == 1 ? LS_THREADS : ncolp;
   for (int col = (nslices == 1 ? threadIdx.x : threadIdx.x % ncolp); col < ntot && slice < nslices; col += col_step) {
     float acc[LS_ROWS];
@@ -202,8 +280,15 @@ extern "C" int32_t gs_sage_layer_small(const float* src, int64_t n_src_rows, int
   prm.seg = *segment_host; prm.include_self = include_self;
   prm.n_parts = n_parts; prm.combine = combine; prm.bias = bias; prm.act = act; prm.l2norm = l2_normalize;
   prm.out = out; prm.ldo = ldo; prm.counter_dev = counter_dev; prm.counter_inc = counter_inc;
+  bool vec = (F % 4 == 0) && (pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && (ntot % 4 == 0) &&
+             (parts_host[0].N % 4 == 0);
+  for (int i = 0; i < n_parts; ++i)
+    vec = vec && (parts_host[i].ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(parts_host[i].B) & 15u) == 0);
+  prm.vec = vec ? 1 : 0;
   const int ncolp = (ntot + 31) & ~31;
-  const int nslices = ncolp <= gs::LS_THREADS ? gs::LS_THREADS / ncolp : 1;
+  const int ncgp = (((ntot + 3) / 4) + 31) & ~31;
+  const int nslices = vec ? (ncgp <= gs::LS_THREADS ? gs::LS_THREADS / ncgp : 1)
+                          : (ncolp <= gs::LS_THREADS ? gs::LS_THREADS / ncolp : 1);
   const size_t smem = (size_t)(2 * gs::LS_ROWS * F + nslices * gs::LS_ROWS * ncolp + gs::LS_ROWS * 16) * sizeof(float);
   GS_REQUIRE(smem <= 200 * 1024, "gs_sage_layer_small: needs %zu bytes of shared memory", smem);
   static bool attr_set = false;
