@@ -180,15 +180,26 @@ __global__ void __launch_bounds__(256) pack_b_kernel(TcParams prm, unsigned char
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, bool ASYNC = false>
 struct TcCfg {
   static constexpr int BK = MODE == 2 ? 64 : 32;             // K elements per block (128 B of operand row)
   static constexpr int UK = MODE == 2 ? 16 : 8;              // UMMA K per instruction (32 B)
   static constexpr int NIMG = MODE == 0 ? 2 : 1;             // hi (+ lo)
   static constexpr int STAGE_BYTES = 2 * NIMG * TC_TILE_BYTES;   // A images then B images
-  static constexpr int STAGES = MODE == 0 ? 3 : 4;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + slack for 1024-B alignment
+  // ASYNC: raw fp32 A K-blocks are staged by cp.async in a ring of RAW_SLOTS slots (RAW_BYTES each) that sits
+  // after the UMMA stages; fewer UMMA stages are needed because the global latency is absorbed by the ring.
+  static constexpr int STAGES = ASYNC ? (MODE == 0 ? 2 : 3) : (MODE == 0 ? 3 : 4);
+  static constexpr int RAW_BYTES = TC_BM * BK * 4;
+  static constexpr int RAW_SLOTS = ASYNC ? (MODE == 2 ? 3 : 4) : 0;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RAW_SLOTS * RAW_BYTES + 1024;  // + slack for 1024-B alignment
 };
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int MODE>
 __device__ __forceinline__ void load_a_chunk(const TcPart& P, int64_t M, int64_t grow, int gcol, bool vec, float (&v)[8]) {
@@ -232,10 +243,10 @@ __device__ __forceinline__ void store_a_chunk(unsigned char* a_img, int row, int
   }
 }
 
-template <int MODE>
+template <int MODE, bool ASYNC>
 __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __grid_constant__ TcParams prm,
                                                                      const unsigned char* __restrict__ ws) {
-  using C = TcCfg<MODE>;
+  using C = TcCfg<MODE, ASYNC>;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_a[C::STAGES], full_b[C::STAGES], empty_bar[C::STAGES], accum_bar;
   __shared__ uint32_t tmem_base_smem;
@@ -256,7 +267,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __gri
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(&full_a[s], TC_PRODUCER_WARPS / 2);   // one arrive per warp of the producing group
+      mbar_init(&full_a[s], ASYNC ? TC_PRODUCER_WARPS : TC_PRODUCER_WARPS / 2);   // one arrive per producing warp
       mbar_init(&full_b[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -274,6 +285,73 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __gri
 
   if (warp < TC_PRODUCER_WARPS) {
     // =============================== A producers ===============================
+    if constexpr (ASYNC) {
+      // All 8 warps share every K-block.  Each thread cp.async's ITS OWN 16-byte chunks of the raw fp32 tile
+      // into a private position of the staging ring (completion is tracked per thread by cp.async groups, so no
+      // cross-thread synchronisation is needed), RAW_SLOTS-1 K-blocks ahead; it then reads them back, splits /
+      // converts, and stores the UMMA tile.
+      constexpr int EPC = MODE == 2 ? 8 : 4;                 // fp32 elements per UMMA 16-byte chunk
+      constexpr int CPT = 4;                                 // UMMA chunks per thread per K-block (1024 / 256)
+      constexpr int RAW_PER_CHUNK = EPC / 4;                 // raw 16-byte pieces per UMMA chunk
+      unsigned char* raw = smem + (size_t)C::STAGES * C::STAGE_BYTES;
+      const int tid = threadIdx.x;                           // 0..255
+      auto locate = [&](int it, int& pi, int& kb) {
+        pi = part_lo; kb = it;
+        while (kb >= prm.p[pi].kblocks) { kb -= prm.p[pi].kblocks; ++pi; }
+      };
+      auto issue = [&](int it) {
+        if (it < total_it) {
+          int pi, kb;
+          locate(it, pi, kb);
+          const TcPart& P = prm.p[pi];
+          unsigned char* slot = raw + (size_t)(it % C::RAW_SLOTS) * C::RAW_BYTES;
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) {
+            const int q = tid + 256 * i;
+            const int row = q >> 3, c = q & 7;
+            const int64_t grow = m0 + row;
+#pragma unroll
+            for (int h = 0; h < RAW_PER_CHUNK; ++h) {
+              const int gcol = kb * C::BK + c * EPC + h * 4;
+              int nbytes = 0;
+              if (grow < prm.M && gcol < P.K) nbytes = min(4, P.K - gcol) * 4;
+              const float* src = nbytes ? (P.A + grow * P.lda + gcol) : P.A;   // always a valid, 16-B aligned address
+              cp_async16(slot + (size_t)(q * RAW_PER_CHUNK + h) * 16, src, nbytes);
+            }
+          }
+        }
+        cp_async_commit();                                   // empty groups keep the group count uniform
+      };
+#pragma unroll
+      for (int j = 0; j < C::RAW_SLOTS - 1; ++j) issue(j);
+      for (int it = 0; it < total_it; ++it) {
+        issue(it + C::RAW_SLOTS - 1);
+        cp_async_wait<C::RAW_SLOTS - 1>();                   // this thread's pieces of K-block `it` have landed
+        const unsigned char* slot = raw + (size_t)(it % C::RAW_SLOTS) * C::RAW_BYTES;
+        float v[CPT][8];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          const int q = tid + 256 * i;
+#pragma unroll
+          for (int h = 0; h < RAW_PER_CHUNK; ++h) {
+            const float4 f = *reinterpret_cast<const float4*>(slot + (size_t)(q * RAW_PER_CHUNK + h) * 16);
+            v[i][h * 4 + 0] = f.x; v[i][h * 4 + 1] = f.y; v[i][h * 4 + 2] = f.z; v[i][h * 4 + 3] = f.w;
+          }
+        }
+        const int s = it % C::STAGES;
+        const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        unsigned char* a_img = smem + (size_t)s * C::STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          const int q = tid + 256 * i;
+          store_a_chunk<MODE>(a_img, q >> 3, q & 7, v[i]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_a[s]);
+      }
+    } else {
     // two groups of 4 warps alternate K-blocks; each thread owns 8 chunks (rows tg>>3 + 16 i, chunk tg & 7)
     const int group = warp >> 2;
     const int tg = threadIdx.x & 127;
@@ -313,6 +391,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __gri
 #pragma unroll
           for (int e = 0; e < 8; ++e) cur[i][e] = nxt[i][e];
       }
+    }
     }
     // =============================== epilogue ===============================
     mbar_wait(&accum_bar, 0);
@@ -444,19 +523,29 @@ static int32_t launch_pack(const TcParams& prm, unsigned char* ws, cudaStream_t 
   return launch_check("pack_b_kernel");
 }
 
-template <int MODE>
-static int32_t launch_tc(const TcParams& prm, const unsigned char* ws, cudaStream_t st) {
-  using C = TcCfg<MODE>;
+template <int MODE, bool ASYNC>
+static int32_t launch_tc_impl(const TcParams& prm, const unsigned char* ws, cudaStream_t st) {
+  using C = TcCfg<MODE, ASYNC>;
   static bool attr_set = false;
   if (!attr_set) {
-    GS_CUDA(cudaFuncSetAttribute(sage_gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    GS_CUDA(cudaFuncSetAttribute(sage_gemm_tc_kernel<MODE, ASYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 C::SMEM_BYTES));
     attr_set = true;
   }
   int tiles_n = prm.p[0].ntiles;
   if (prm.combine == GS_COMBINE_CONCAT && prm.n_parts == 2) tiles_n += prm.p[1].ntiles;
   dim3 grid((unsigned)((prm.M + TC_BM - 1) / TC_BM), (unsigned)tiles_n);
-  sage_gemm_tc_kernel<MODE><<<grid, TC_THREADS, C::SMEM_BYTES, st>>>(prm, ws);
+  sage_gemm_tc_kernel<MODE, ASYNC><<<grid, TC_THREADS, C::SMEM_BYTES, st>>>(prm, ws);
   return launch_check("sage_gemm_tc_kernel");
+}
+
+template <int MODE>
+static int32_t launch_tc(const TcParams& prm, const unsigned char* ws, cudaStream_t st) {
+  bool aligned = true;                         // cp.async needs 16-byte aligned rows
+  for (int i = 0; i < prm.n_parts; ++i)
+    aligned = aligned && (prm.p[i].lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(prm.p[i].A) & 15u) == 0);
+  if (aligned && tuning("gemm_async", 1)) return launch_tc_impl<MODE, true>(prm, ws, st);
+  return launch_tc_impl<MODE, false>(prm, ws, st);
 }
 
 int32_t sage_gemm_tc_pack(const gs_gemm_part* parts, int32_t n_parts, int32_t math, void* workspace, cudaStream_t st) {

@@ -8,7 +8,7 @@
 
 namespace gs {
 
-constexpr int LS_ROWS = 8;
+constexpr int LS_ROWS = 4;
 constexpr int LS_THREADS = 512;
 
 struct LsParams {
@@ -146,10 +146,19 @@ __global__ void __launch_bounds__(LS_THREADS) sage_layer_small_kernel(const __gr
         const float* w = P.B + c;
         const int kchunk = (((P.K + nslices - 1) / nslices) + 3) & ~3;
         const int kbeg = sl * kchunk, kend = min(P.K, kbeg + kchunk);   // K % 4 == 0 in the vector path
+        float4 wn[4];                                    // software pipeline: next k-step's weights are in flight
+        if (kbeg < kend) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) wn[u] = __ldg(reinterpret_cast<const float4*>(w + (int64_t)(kbeg + u) * P.ldb));
+        }
         for (int kk = kbeg; kk < kend; kk += 4) {
           float4 wv[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) wv[u] = __ldg(reinterpret_cast<const float4*>(w + (int64_t)(kk + u) * P.ldb));
+          for (int u = 0; u < 4; ++u) wv[u] = wn[u];
+          if (kk + 4 < kend) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) wn[u] = __ldg(reinterpret_cast<const float4*>(w + (int64_t)(kk + 4 + u) * P.ldb));
+          }
 #pragma unroll
           for (int r = 0; r < LS_ROWS; ++r) {
             const float4 xv = *reinterpret_cast<const float4*>(x + r * F + kk);

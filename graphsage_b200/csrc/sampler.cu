@@ -61,7 +61,7 @@ struct KhopParams {
   int32_t n_hops;
 };
 
-__global__ void __launch_bounds__(256) sample_padded_khop_kernel(const int32_t* __restrict__ adj, int64_t n_rows,
+__global__ void __launch_bounds__(512) sample_padded_khop_kernel(const int32_t* __restrict__ adj, int64_t n_rows,
                                                                  int32_t max_deg, const int32_t* __restrict__ seeds,
                                                                  const __grid_constant__ KhopParams kp, uint64_t seed,
                                                                  uint64_t counter,
@@ -72,16 +72,22 @@ __global__ void __launch_bounds__(256) sample_padded_khop_kernel(const int32_t* 
   if (warp < kp.n_hops) {
     for (int j = lane; j < max_deg; j += 32) perm[warp][j] = (int16_t)j;
     __syncwarp();
+    // the k draws are independent Philox blocks: lanes compute them in parallel (draw i = word i&3 of block i>>2),
+    // then lane 0 runs the short serial swap chain
+    const uint64_t ctr = counter + (counter_dev ? *counter_dev : 0ull) + (uint64_t)warp;
+    const int k = kp.fanout[warp];
+    for (int blk = lane; blk * 4 < k; blk += 32) {
+      u32x4 c{(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, kStreamPadded + (uint32_t)blk};
+      u32x4 r = philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+      pi[warp][blk * 4 + 0] = (int32_t)r.x;
+      if (blk * 4 + 1 < 64) pi[warp][blk * 4 + 1] = (int32_t)r.y;
+      if (blk * 4 + 2 < 64) pi[warp][blk * 4 + 2] = (int32_t)r.z;
+      if (blk * 4 + 3 < 64) pi[warp][blk * 4 + 3] = (int32_t)r.w;
+    }
+    __syncwarp();
     if (lane == 0) {
-      const uint64_t ctr = counter + (counter_dev ? *counter_dev : 0ull) + (uint64_t)warp;
-      const int k = kp.fanout[warp];
-      u32x4 r{0, 0, 0, 0};
       for (int i = 0; i < k; ++i) {
-        if ((i & 3) == 0) {
-          u32x4 c{(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, kStreamPadded + (uint32_t)(i >> 2)};
-          r = philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-        }
-        int j = i + (int)mulhi32(pick(r, i & 3), (uint32_t)(max_deg - i));
+        int j = i + (int)mulhi32((uint32_t)pi[warp][i], (uint32_t)(max_deg - i));
         int16_t t = perm[warp][i];
         perm[warp][i] = perm[warp][j];
         perm[warp][j] = t;
@@ -201,10 +207,10 @@ int32_t gs_sample_padded_khop(const int32_t* adj, int64_t n_rows, int32_t max_de
     kp.out[t] = out_host[t];
     total += cnt;
   }
-  int64_t blocks = (total + 255) / 256;
-  int64_t cap = (int64_t)gs::sm_count() * 8;
+  int64_t blocks = (total + 511) / 512;
+  int64_t cap = (int64_t)gs::sm_count() * 2;             // few, fat blocks: each block rebuilds the permutations once
   if (blocks > cap) blocks = cap;
-  gs::sample_padded_khop_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(adj, n_rows, max_deg, seeds, kp, seed,
+  gs::sample_padded_khop_kernel<<<(unsigned)blocks, 512, 0, (cudaStream_t)stream>>>(adj, n_rows, max_deg, seeds, kp, seed,
                                                                                     counter, counter_dev);
   return gs::launch_check("sample_padded_khop_kernel");
 }
