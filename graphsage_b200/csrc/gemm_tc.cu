@@ -185,13 +185,17 @@ struct TcCfg {
   static constexpr int BK = MODE == 2 ? 64 : 32;             // K elements per block (128 B of operand row)
   static constexpr int UK = MODE == 2 ? 16 : 8;              // UMMA K per instruction (32 B)
   static constexpr int NIMG = MODE == 0 ? 2 : 1;             // hi (+ lo)
-  static constexpr int STAGE_BYTES = 2 * NIMG * TC_TILE_BYTES;   // A images then B images
-  // ASYNC: raw fp32 A K-blocks are staged by cp.async in a ring of RAW_SLOTS slots (RAW_BYTES each) that sits
-  // after the UMMA stages; fewer UMMA stages are needed because the global latency is absorbed by the ring.
-  static constexpr int STAGES = ASYNC ? (MODE == 0 ? 2 : 3) : (MODE == 0 ? 3 : 4);
+  static constexpr int IMG_BYTES = NIMG * TC_TILE_BYTES;     // one operand's images for one K-block
+  // A and B have SEPARATE rings.  A is refilled by the producer warps (their prefetch lives in registers / the
+  // raw ring, so few stages suffice).  B tiles come straight from L2 by bulk copy, and a copy can only be posted
+  // once its slot is free - so the B ring is deep enough to cover the L2 -> shared latency (NB copies in flight).
+  static constexpr int SA = MODE == 0 ? 2 : 3;
+  static constexpr int NB = ASYNC ? (MODE == 0 ? 2 : 4) : (MODE == 0 ? 4 : 8);
   static constexpr int RAW_BYTES = TC_BM * BK * 4;
   static constexpr int RAW_SLOTS = ASYNC ? (MODE == 2 ? 3 : 4) : 0;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RAW_SLOTS * RAW_BYTES + 1024;  // + slack for 1024-B alignment
+  static constexpr int B_OFF = SA * IMG_BYTES;
+  static constexpr int RAW_OFF = B_OFF + NB * IMG_BYTES;
+  static constexpr int SMEM_BYTES = RAW_OFF + RAW_SLOTS * RAW_BYTES + 1024;  // + slack for 1024-B alignment
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
@@ -248,7 +252,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __gri
                                                                      const unsigned char* __restrict__ ws) {
   using C = TcCfg<MODE, ASYNC>;
   extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full_a[C::STAGES], full_b[C::STAGES], empty_bar[C::STAGES], accum_bar;
+  __shared__ __align__(8) uint64_t full_a[C::SA], empty_a[C::SA], full_b[C::NB], empty_b[C::NB], accum_bar;
   __shared__ uint32_t tmem_base_smem;
 
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -266,10 +270,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __gri
   for (int pi = part_lo; pi < part_hi; ++pi) total_it += prm.p[pi].kblocks;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::STAGES; ++s) {
+    for (int s = 0; s < C::SA; ++s) {
       mbar_init(&full_a[s], ASYNC ? TC_PRODUCER_WARPS : TC_PRODUCER_WARPS / 2);   // one arrive per producing warp
+      mbar_init(&empty_a[s], 1);
+    }
+    for (int s = 0; s < C::NB; ++s) {
       mbar_init(&full_b[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_b[s], 1);
     }
     mbar_init(&accum_bar, 1);
     fence_mbar_init();
@@ -293,7 +300,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __gri
       constexpr int EPC = MODE == 2 ? 8 : 4;                 // fp32 elements per UMMA 16-byte chunk
       constexpr int CPT = 4;                                 // UMMA chunks per thread per K-block (1024 / 256)
       constexpr int RAW_PER_CHUNK = EPC / 4;                 // raw 16-byte pieces per UMMA chunk
-      unsigned char* raw = smem + (size_t)C::STAGES * C::STAGE_BYTES;
+      unsigned char* raw = smem + C::RAW_OFF;
       const int tid = threadIdx.x;                           // 0..255
       auto locate = [&](int it, int& pi, int& kb) {
         pi = part_lo; kb = it;
@@ -338,10 +345,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __gri
             v[i][h * 4 + 0] = f.x; v[i][h * 4 + 1] = f.y; v[i][h * 4 + 2] = f.z; v[i][h * 4 + 3] = f.w;
           }
         }
-        const int s = it % C::STAGES;
-        const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        unsigned char* a_img = smem + (size_t)s * C::STAGE_BYTES;
+        const int s = it % C::SA;
+        const uint32_t ph = (uint32_t)(it / C::SA) & 1u;
+        mbar_wait(&empty_a[s], ph ^ 1u);
+        unsigned char* a_img = smem + (size_t)s * C::IMG_BYTES;
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {
           const int q = tid + 256 * i;
@@ -373,13 +380,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __gri
     int it = group;
     if (it < total_it) fetch(it, cur);
     for (; it < total_it; it += 2) {
-      const int s = it % C::STAGES;
-      const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
+      const int s = it % C::SA;
+      const uint32_t ph = (uint32_t)(it / C::SA) & 1u;
       float nxt[8][8];
       const bool more = it + 2 < total_it;
       if (more) fetch(it + 2, nxt);                    // prefetch this group's next K-block
-      mbar_wait(&empty_bar[s], ph ^ 1u);
-      unsigned char* a_img = smem + (size_t)s * C::STAGE_BYTES;
+      mbar_wait(&empty_a[s], ph ^ 1u);
+      unsigned char* a_img = smem + (size_t)s * C::IMG_BYTES;
 #pragma unroll
       for (int i = 0; i < 8; ++i) store_a_chunk<MODE>(a_img, r0 + 16 * i, c, cur[i]);
       fence_proxy_async();                             // generic-proxy stores -> visible to the MMA (async proxy)
@@ -433,14 +440,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __gri
     // =============================== MMA issuer ===============================
     constexpr uint32_t idesc = make_idesc(MODE == 2 ? 1u : 2u, TC_BM, TC_BN);
     for (int it = 0; it < total_it; ++it) {
-      const int s = it % C::STAGES;
-      const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
-      mbar_wait(&full_a[s], ph);
-      mbar_wait(&full_b[s], ph);
+      const int s = it % C::SA, sb = it % C::NB;
+      mbar_wait(&full_a[s], (uint32_t)(it / C::SA) & 1u);
+      mbar_wait(&full_b[sb], (uint32_t)(it / C::NB) & 1u);
       tc_fence_after();
       if (lane == 0) {
-        const uint32_t a_base = smem_u32(smem + (size_t)s * C::STAGE_BYTES);
-        const uint32_t b_base = a_base + C::NIMG * TC_TILE_BYTES;
+        const uint32_t a_base = smem_u32(smem + (size_t)s * C::IMG_BYTES);
+        const uint32_t b_base = smem_u32(smem + C::B_OFF + (size_t)sb * C::IMG_BYTES);
         const uint64_t a_hi = make_smem_desc(a_base), b_hi = make_smem_desc(b_base);
 #pragma unroll
         for (int k = 0; k < C::BK / C::UK; ++k) {
@@ -453,7 +459,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __gri
             umma_ss<false>(tmem_acc, a_lo + koff, b_hi + koff, idesc, 1u);
           }
         }
-        umma_commit(&empty_bar[s]);                                  // stage reusable once these MMAs retire
+        umma_commit(&empty_a[s]);                                    // A stage and B slot reusable once these MMAs retire
+        umma_commit(&empty_b[sb]);
         if (it == total_it - 1) umma_commit(&accum_bar);             // accumulator complete
       }
       __syncwarp();
@@ -466,12 +473,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __gri
         const TcPart& P = prm.p[pi];
         const unsigned char* base = ws + P.img_off + (int64_t)ntile * P.kblocks * C::NIMG * TC_TILE_BYTES;
         for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
-          const int s = it % C::STAGES;
-          const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
-          mbar_wait(&empty_bar[s], ph ^ 1u);
-          mbar_expect_tx(&full_b[s], C::NIMG * TC_TILE_BYTES);
-          bulk_g2s(smem + (size_t)s * C::STAGE_BYTES + C::NIMG * TC_TILE_BYTES,
-                   base + (int64_t)kb * C::NIMG * TC_TILE_BYTES, C::NIMG * TC_TILE_BYTES, &full_b[s]);
+          const int sb = it % C::NB;
+          const uint32_t ph = (uint32_t)(it / C::NB) & 1u;
+          mbar_wait(&empty_b[sb], ph ^ 1u);
+          mbar_expect_tx(&full_b[sb], C::IMG_BYTES);
+          bulk_g2s(smem + C::B_OFF + (size_t)sb * C::IMG_BYTES, base + (int64_t)kb * C::IMG_BYTES, C::IMG_BYTES,
+                   &full_b[sb]);
         }
       }
     }
@@ -544,7 +551,7 @@ static int32_t launch_tc(const TcParams& prm, const unsigned char* ws, cudaStrea
   bool aligned = true;                         // cp.async needs 16-byte aligned rows
   for (int i = 0; i < prm.n_parts; ++i)
     aligned = aligned && (prm.p[i].lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(prm.p[i].A) & 15u) == 0);
-  if (aligned && tuning("gemm_async", 1)) return launch_tc_impl<MODE, true>(prm, ws, st);
+  if (aligned && tuning("gemm_async", 0)) return launch_tc_impl<MODE, true>(prm, ws, st);
   return launch_tc_impl<MODE, false>(prm, ws, st);
 }
 
