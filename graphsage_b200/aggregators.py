@@ -201,9 +201,45 @@ class MaxPoolingAggregator(_SageAggregator):
         return self._finish([(self_vecs, self.input_dim, self.vars["self_weights"]),
                              (hmax, self.hidden_dim, self.vars["neigh_weights"])], self._combine())
 
+    def _bf16_table(self, src):
+        """bf16 copy of an fp32 source with a 16-byte-multiple row pitch (cached per source tensor version)."""
+        if src.dtype == torch.bfloat16:
+            return src
+        key = (src.data_ptr(), src._version, tuple(src.shape))
+        if getattr(self, "_bf16_key", None) != key:
+            t = torch.zeros((src.shape[0], ops.pad_cols(src.shape[1])), dtype=torch.bfloat16, device=src.device)
+            t[:, :src.shape[1]] = src
+            self._bf16_src, self._bf16_key = t[:, :src.shape[1]], key
+        return self._bf16_src
+
+    def _fused_ok(self, src, segments):
+        return (self.math == ops.MATH_BF16 and torch.is_tensor(src) and not self.dropout and len(self.mlp_layers) == 1
+                and self.neigh_input_dim <= 640 and self.hidden_dim % 128 == 0 and all(s.k <= 128 for s in segments)
+                and self.mlp_layers[0].act is relu and "bias" in self.mlp_layers[0].vars)
+
     def aggregate_rows(self, src, segments, final=None):
         rows = max(s.out_row0 + s.n for s in segments)
         dev = src.device
+        if self._fused_ok(src, segments):
+            # K4: gather -> MLP -> ReLU -> max over the fanout in one tcgen05 kernel per hop (bf16 operands)
+            table = self._bf16_table(src)
+            if getattr(self, "_packed_mlp", None) is None:
+                self._packed_mlp = ops.PackedMlpWeights()
+            mlp = self.mlp_layers[0]
+            F_in = src.shape[1]
+            xs = torch.empty((rows, ops.pad_cols(F_in)), dtype=torch.float32, device=dev)[:, :F_in]
+            hmax = torch.empty((rows, self.hidden_dim), dtype=torch.float32, device=dev)
+            for s in segments:
+                n = s.n
+                h = ops.maxpool_mlp_fused(table, n, s.k, mlp.vars["weights"], mlp.vars["bias"], self._packed_mlp,
+                                          row_ids=s.neigh_ids, row0=s.neigh_row0, K=self.neigh_input_dim)
+                hmax[s.out_row0:s.out_row0 + n] = h
+                if s.self_ids is not None:
+                    xs[s.out_row0:s.out_row0 + n] = ops.gather_rows(src, s.self_ids[:n]).float()
+                else:
+                    xs[s.out_row0:s.out_row0 + n] = src[s.self_row0:s.self_row0 + n].float()
+            return self._finish([(xs, self.input_dim, self.vars["self_weights"]),
+                                 (hmax, self.hidden_dim, self.vars["neigh_weights"])], self._combine())
         xs = torch.empty((rows, ops.pad_cols(src.shape[1])), dtype=torch.float32, device=dev)[:, :src.shape[1]]
         hmax = torch.empty((rows, self.hidden_dim), dtype=torch.float32, device=dev)
         for s in segments:

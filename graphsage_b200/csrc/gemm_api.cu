@@ -8,6 +8,7 @@ int64_t sage_gemm_tc_workspace(int64_t M, const gs_gemm_part* parts, int32_t n_p
 int32_t sage_gemm_tc(int64_t M, const gs_gemm_part* parts, int32_t n_parts, int32_t combine, const float* bias,
                      int32_t act, int32_t math, float* out, int64_t ldo, const void* workspace, cudaStream_t st);
 int32_t sage_gemm_tc_pack(const gs_gemm_part* parts, int32_t n_parts, int32_t math, void* workspace, cudaStream_t st);
+int32_t tc_debug_read(unsigned long long* out_host, int n);
 }  // namespace gs
 
 static int32_t check_parts(int64_t M, const gs_gemm_part* parts, int32_t n_parts, int32_t combine) {
@@ -57,6 +58,9 @@ int32_t gs_sage_gemm_prepacked(int64_t M, const gs_gemm_part* parts_host, int32_
   GS_REQUIRE(is_tc(math), "gs_sage_gemm: unknown math mode %d", math);
   return gs::sage_gemm_tc(M, parts_host, n_parts, combine, bias, act, math, out, ldo, workspace, (cudaStream_t)stream);
 }
+
+/* developer probe (not part of the public header): timeline stamps of CTA (0,0) of the last tcgen05 GEMM */
+int32_t gs_debug_read_gemm_timeline(unsigned long long* out_host, int32_t n) { return gs::tc_debug_read(out_host, n); }
 
 int32_t gs_sage_gemm(int64_t M, const gs_gemm_part* parts_host, int32_t n_parts, int32_t combine, const float* bias,
                      int32_t act, int32_t math, float* out, int64_t ldo, void* workspace, void* stream) {

@@ -16,15 +16,10 @@
 //              pack_b_kernel into the caller's workspace) with mbarrier complete_tx.
 // A goes through registers on purpose: the hi/lo split (and the bf16 rounding) is arithmetic on the
 // operand, and the same producer slot later takes a row-id indirection (gather-A) for the max-pool MLP.
-#include <cuda_bf16.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace gs {
 
-constexpr int TC_BM = 128;       // UMMA M (cta_group::1)
-constexpr int TC_BN = 128;       // UMMA N
-constexpr int TC_TILE_BYTES = TC_BM * 128;   // one operand tile image: 128 rows x 128 B (one SW128 atom wide)
 constexpr int TC_PRODUCER_WARPS = 8;
 constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 2) * 32;
 
@@ -51,85 +46,6 @@ struct TcParams {
   int64_t ldo;
   int32_t tiles_n0;    // number of N tiles of part 0 (CONCAT tile -> part mapping)
 };
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers (tcgen05 / TMEM)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-
-template <bool kBf16>
-__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  if constexpr (kBf16) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  }
-}
-
-// 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane base + t)
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
-//   [0,14) start address >> 4, [16,30) LBO >> 4 (= 1, unused for swizzled K-major),
-//   [32,46) SBO >> 4 (8 rows x 128 B = 1024 B -> 64), [46,48) version = 1, [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
-// cute::UMMA::InstrDescriptor: [4,6) c_format (1 = F32), [7,10) a_format, [10,13) b_format
-// (F16 = 0, BF16 = 1, TF32 = 2), [15] a_major (0 = K), [16] b_major (0 = K), [17,23) N >> 3, [24,29) M >> 4
-__host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint32_t N) {
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
-}
-
-__device__ __forceinline__ uint32_t tf32_mask(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
-
-// byte offset of 16-byte chunk c (0..7) of row r (0..127) inside a SW128 K-major tile image
-__host__ __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
-  return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
-}
 
 // ---------------------------------------------------------------------------------------------
 // B packing: weights [K, N] row-major fp32 -> per (n tile, k block) tile images of W^T
@@ -180,6 +96,16 @@ __global__ void __launch_bounds__(256) pack_b_kernel(TcParams prm, unsigned char
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
+// timeline probe (CTA (0,0) only): globaltimer stamps at pipeline milestones, read back by gs_debug_read
+__device__ unsigned long long g_tc_dbg[32];
+__device__ __forceinline__ void dbg_stamp(int slot) {
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_tc_dbg[slot] = t;
+  }
+}
+
 template <int MODE, bool ASYNC = false>
 struct TcCfg {
   static constexpr int BK = MODE == 2 ? 64 : 32;             // K elements per block (128 B of operand row)
@@ -198,12 +124,6 @@ struct TcCfg {
   static constexpr int SMEM_BYTES = RAW_OFF + RAW_SLOTS * RAW_BYTES + 1024;  // + slack for 1024-B alignment
 };
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int MODE>
 __device__ __forceinline__ void load_a_chunk(const TcPart& P, int64_t M, int64_t grow, int gcol, bool vec, float (&v)[8]) {
@@ -257,6 +177,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __gri
 
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) dbg_stamp(0);
 
   // ---- which output tile, which parts feed it
   const int64_t m0 = (int64_t)blockIdx.x * TC_BM;
@@ -289,6 +210,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = tmem_base_smem;
+  if (threadIdx.x == 0) dbg_stamp(1);
 
   if (warp < TC_PRODUCER_WARPS) {
     // =============================== A producers ===============================
@@ -392,6 +314,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __gri
       fence_proxy_async();                             // generic-proxy stores -> visible to the MMA (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_a[s]);
+      if (threadIdx.x == 0 && it == 0) dbg_stamp(2);
+      if (threadIdx.x == 0 && it + 2 >= total_it) dbg_stamp(3);
       if (more) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -401,8 +325,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __gri
     }
     }
     // =============================== epilogue ===============================
+    if (threadIdx.x == 0) dbg_stamp(4);
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
+    if (threadIdx.x == 0) dbg_stamp(5);
     const int q = warp & 3;                           // TMEM lane quarter this warp may touch
     const int half = warp >> 2;                       // columns [64*half, 64*half + 64)
     const int64_t grow = m0 + q * 32 + lane;
@@ -436,14 +362,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __gri
       }
     }
     tc_fence_before();
+    if (threadIdx.x == 0) dbg_stamp(6);
   } else if (warp == TC_PRODUCER_WARPS) {
     // =============================== MMA issuer ===============================
     constexpr uint32_t idesc = make_idesc(MODE == 2 ? 1u : 2u, TC_BM, TC_BN);
     for (int it = 0; it < total_it; ++it) {
       const int s = it % C::SA, sb = it % C::NB;
       mbar_wait(&full_a[s], (uint32_t)(it / C::SA) & 1u);
+      if (lane == 0 && it == 0) dbg_stamp(8);
       mbar_wait(&full_b[sb], (uint32_t)(it / C::NB) & 1u);
       tc_fence_after();
+      if (lane == 0 && it == 0) dbg_stamp(9);
+      if (lane == 0 && it == 1) dbg_stamp(10);
+      if (lane == 0 && it == 8) dbg_stamp(11);
+      if (lane == 0 && it == total_it - 1) dbg_stamp(12);
       if (lane == 0) {
         const uint32_t a_base = smem_u32(smem + (size_t)s * C::IMG_BYTES);
         const uint32_t b_base = smem_u32(smem + C::B_OFF + (size_t)sb * C::IMG_BYTES);
@@ -462,6 +394,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __gri
         umma_commit(&empty_a[s]);                                    // A stage and B slot reusable once these MMAs retire
         umma_commit(&empty_b[sb]);
         if (it == total_it - 1) umma_commit(&accum_bar);             // accumulator complete
+        if (it == total_it - 1) dbg_stamp(13);
       }
       __syncwarp();
     }
@@ -485,6 +418,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __gri
     __syncwarp();
   }
   __syncthreads();
+  if (threadIdx.x == 0) dbg_stamp(7);
   if (warp == TC_PRODUCER_WARPS) {
     tc_fence_after();
     tmem_dealloc(tmem_acc, TC_BN);
@@ -553,6 +487,13 @@ static int32_t launch_tc(const TcParams& prm, const unsigned char* ws, cudaStrea
     aligned = aligned && (prm.p[i].lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(prm.p[i].A) & 15u) == 0);
   if (aligned && tuning("gemm_async", 0)) return launch_tc_impl<MODE, true>(prm, ws, st);
   return launch_tc_impl<MODE, false>(prm, ws, st);
+}
+
+int32_t tc_debug_read(unsigned long long* out_host, int n) {
+  if (n > 32) n = 32;
+  GS_CUDA(cudaDeviceSynchronize());
+  GS_CUDA(cudaMemcpyFromSymbol(out_host, g_tc_dbg, sizeof(unsigned long long) * n));
+  return GS_OK;
 }
 
 int32_t sage_gemm_tc_pack(const gs_gemm_part* parts, int32_t n_parts, int32_t math, void* workspace, cudaStream_t st) {

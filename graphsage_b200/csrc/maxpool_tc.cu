@@ -1,0 +1,287 @@
+// K4: the max-pool aggregator's neighbour branch as ONE kernel on tcgen05 (bf16 operands, fp32 accumulate):
+//   out[g, h] = max_{j<k} relu( table[row(g, j), :] . Wm[:, h] + bm[h] )
+//   reference graphsage/aggregators.py:176-182 (reshape -> Dense(relu, bias) -> reshape -> reduce_max) with
+//   graphsage/layers.py:104-116 and the feature gather of graphsage/models.py:299 fused in front of it:
+//   neither the gathered [n*k, F] rows nor the [n*k, hidden] MLP activations ever touch HBM.
+//
+// Persistent CTAs.  A CTA owns one 128-wide slice of the hidden dimension for its whole life: that slice of
+// Wm^T (<= 10 K-blocks x 16 KB, pre-swizzled bf16 tile images) is bulk-copied into shared memory ONCE and stays
+// resident.  The CTA then walks M tiles (G = floor(128 / k) whole fanout groups per tile, zero rows after them):
+//   warps 0-3  gather-A producers: cp.async 16-byte pieces of the addressed table rows straight into the UMMA
+//              K-major SWIZZLE_128B tile (bf16 in the table = bf16 in the tile: no conversion), 2 K-blocks ahead
+//   warp  4    MMA issuer: tcgen05.mma.kind::f16 (M128 N128 K16), accumulators double-buffered in TMEM
+//   warp  5    loads the resident weight slice (cp.async.bulk + mbarrier)
+//   warps 6-9  epilogue: tcgen05.ld -> + bias -> ReLU -> staged transpose in shared memory -> max over the k rows
+//              of each group -> coalesced store; overlaps the next tile's MMAs (second TMEM buffer)
+#include "tc_common.cuh"
+
+namespace gs {
+
+constexpr int MP_SA = 3;                      // A stages (16 KB each)
+constexpr int MP_MAX_KB = 10;                 // resident weight K-blocks (K <= 640)
+constexpr int MP_THREADS = 320;
+constexpr int MP_STAGE_LD = 129;              // padded row length of the epilogue staging [32][129]
+constexpr int MP_SMEM = MP_MAX_KB * TC_TILE_BYTES + MP_SA * TC_TILE_BYTES + 32 * MP_STAGE_LD * 4 + 1024;
+
+struct MpParams {
+  const __nv_bfloat16* table;   // [n_rows, pitch]
+  int64_t n_rows, pitch;
+  int32_t K, kblocks;
+  const int32_t* row_ids;       // [n_groups * k] or NULL
+  int64_t row0;                 // used when row_ids == NULL: row(g, j) = row0 + g*k + j
+  int64_t n_groups;
+  int32_t k, G;                 // fanout, groups per tile
+  int64_t n_tiles;
+  int32_t hidden, n_slices;
+  const unsigned char* wimg;    // packed Wm^T: [n_slices][kblocks][16 KB]
+  const float* bias;            // [hidden] or NULL
+  float* out;                   // [n_groups, hidden]
+  int64_t ldo;
+};
+
+// Wm [K, hidden] row-major fp32 -> bf16 tile images of Wm^T (128 hidden rows x 64 k, K-major, SW128)
+__global__ void __launch_bounds__(256) maxpool_pack_kernel(const float* __restrict__ W, int64_t ldw, int K, int hidden,
+                                                           int kblocks, unsigned char* __restrict__ img) {
+  const int slice = blockIdx.x / kblocks, kb = blockIdx.x % kblocks;
+  unsigned char* dst = img + ((int64_t)slice * kblocks + kb) * TC_TILE_BYTES;
+  for (int q = threadIdx.x; q < 128 * 8; q += blockDim.x) {
+    const int c = q >> 7, n = q & 127;
+    const int gn = slice * 128 + n, k0 = kb * 64 + c * 8;
+    __nv_bfloat162 h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float a = (gn < hidden && k0 + 2 * e < K) ? W[(int64_t)(k0 + 2 * e) * ldw + gn] : 0.f;
+      float b = (gn < hidden && k0 + 2 * e + 1 < K) ? W[(int64_t)(k0 + 2 * e + 1) * ldw + gn] : 0.f;
+      h[e] = __floats2bfloat162_rn(a, b);
+    }
+    *reinterpret_cast<uint4*>(dst + sw128_off(n, c)) = *reinterpret_cast<uint4*>(h);
+  }
+}
+
+__global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid_constant__ MpParams prm) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_a[MP_SA], empty_a[MP_SA], acc_full[2], acc_empty[2], b_full;
+  __shared__ uint32_t tmem_base_smem;
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* b_res = smem;                                        // resident weight slice
+  unsigned char* a_ring = smem + MP_MAX_KB * TC_TILE_BYTES;
+  float* stage = reinterpret_cast<float*>(a_ring + MP_SA * TC_TILE_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x % prm.n_slices;
+  const int64_t tile0 = blockIdx.x / prm.n_slices, tile_step = gridDim.x / prm.n_slices;
+  const int kblocks = prm.kblocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MP_SA; ++s) {
+      mbar_init(&full_a[s], 4);           // one arrive per producer warp
+      mbar_init(&empty_a[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);        // one arrive per epilogue warp
+    }
+    mbar_init(&b_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(&tmem_base_smem, 256);     // two 128-column fp32 accumulators
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp < 4) {
+    // =============================== gather-A producers ===============================
+    const int tid = threadIdx.x;                    // 0..127
+    const int c = tid & 7, r0 = tid >> 3;           // chunk column, first row; rows r0 + 16 i
+    const int rows_valid = prm.G * prm.k;
+    uint32_t it = 0;                                // running K-block counter across tiles (stage / phase)
+    int pending = 0;                                // K-blocks issued but not yet published
+    // pipeline state for publishing: we publish K-block (it - 2) after issuing K-block it
+    auto publish = [&](uint32_t which) {
+      const int s = which % MP_SA;
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_a[s]);
+    };
+    for (int64_t t = tile0; t < prm.n_tiles; t += tile_step) {
+      const __nv_bfloat16* rowp[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = r0 + 16 * i;
+        const int64_t flat = t * rows_valid + r;    // index into the (group, j) row list
+        rowp[i] = nullptr;
+        if (r < rows_valid && flat < prm.n_groups * prm.k) {
+          int64_t id = prm.row_ids ? (int64_t)prm.row_ids[flat] : prm.row0 + flat;
+          if (id < 0 || id >= prm.n_rows) id = prm.n_rows - 1;
+          rowp[i] = prm.table + id * prm.pitch;
+        }
+      }
+      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const int s = it % MP_SA;
+        mbar_wait(&empty_a[s], ((it / MP_SA) & 1u) ^ 1u);
+        unsigned char* a_img = a_ring + (size_t)s * TC_TILE_BYTES;
+        const int col = kb * 64 + c * 8;            // first bf16 column of this 16-byte piece
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int nbytes = 0;
+          if (rowp[i] != nullptr && col < prm.K) nbytes = min(8, prm.K - col) * 2;
+          const void* src = nbytes ? (const void*)(rowp[i] + col) : (const void*)prm.table;
+          cp_async16(a_img + sw128_off(r0 + 16 * i, c), src, nbytes);
+        }
+        cp_async_commit();
+        ++pending;
+        if (pending == 3) {                         // two K-blocks stay in flight; the oldest is complete now
+          cp_async_wait<2>();
+          publish(it - 2);
+          --pending;
+        }
+      }
+    }
+    // drain
+    if (pending == 2) { cp_async_wait<1>(); publish(it - 2); --pending; }
+    if (pending == 1) { cp_async_wait<0>(); publish(it - 1); --pending; }
+  } else if (warp == 4) {
+    // =============================== MMA issuer ===============================
+    constexpr uint32_t idesc = make_idesc(1u, TC_BM, TC_BN);          // bf16 x bf16 -> fp32
+    mbar_wait(&b_full, 0);
+    uint32_t it = 0, tcount = 0;
+    for (int64_t t = tile0; t < prm.n_tiles; t += tile_step, ++tcount) {
+      const uint32_t buf = tcount & 1u;
+      mbar_wait(&acc_empty[buf], ((tcount >> 1) & 1u) ^ 1u);          // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * 128u;
+      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const int s = it % MP_SA;
+        mbar_wait(&full_a[s], (it / MP_SA) & 1u);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t adesc = make_smem_desc(smem_u32(a_ring + (size_t)s * TC_TILE_BYTES));
+          const uint64_t bdesc = make_smem_desc(smem_u32(b_res + (size_t)kb * TC_TILE_BYTES));
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            umma_ss<true>(tmem_acc, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), idesc, (kb > 0 || k4 > 0) ? 1u : 0u);
+          umma_commit(&empty_a[s]);
+          if (kb == kblocks - 1) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 5) {
+    // =============================== resident weight slice ===============================
+    if (lane == 0) {
+      mbar_expect_tx(&b_full, (uint32_t)(kblocks * TC_TILE_BYTES));
+      const unsigned char* src = prm.wimg + (int64_t)slice * kblocks * TC_TILE_BYTES;
+      for (int kb = 0; kb < kblocks; ++kb)
+        bulk_g2s(b_res + (size_t)kb * TC_TILE_BYTES, src + (int64_t)kb * TC_TILE_BYTES, TC_TILE_BYTES, &b_full);
+    }
+    __syncwarp();
+  } else {
+    // =============================== epilogue ===============================
+    const int et = threadIdx.x - 192;               // 0..127
+    const int q = warp & 3;                         // TMEM lane quarter of this warp (warps 6,7,8,9 -> 2,3,0,1)
+    const int row = q * 32 + lane;                  // tile row held by this thread
+    const int k = prm.k, G = prm.G;
+    uint32_t tcount = 0;
+    for (int64_t t = tile0; t < prm.n_tiles; t += tile_step, ++tcount) {
+      const uint32_t buf = tcount & 1u;
+      mbar_wait(&acc_full[buf], (tcount >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * 128u + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int cb = 0; cb < 4; ++cb) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_acc + (uint32_t)(cb * 32), r);
+        tmem_ld_wait();
+        const int hcol0 = slice * 128 + cb * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float v = __uint_as_float(r[j]);
+          if (prm.bias) v += prm.bias[hcol0 + j];
+          stage[j * MP_STAGE_LD + row] = fmaxf(v, 0.f);               // ReLU (Dense act, aggregators.py:147)
+        }
+        named_bar_sync(1, 128);
+        // (column cc, group g) work items: max over the group's k consecutive rows
+        for (int w = et; w < 32 * G; w += 128) {
+          const int cc = w & 31, g = w >> 5;
+          const int64_t gg = t * G + g;
+          if (gg < prm.n_groups) {
+            const float* p = stage + cc * MP_STAGE_LD + g * k;
+            float m = p[0];
+            for (int j = 1; j < k; ++j) m = fmaxf(m, p[j]);
+            prm.out[gg * prm.ldo + hcol0 + cc] = m;
+          }
+        }
+        named_bar_sync(1, 128);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+}  // namespace gs
+
+extern "C" {
+
+int64_t gs_maxpool_mlp_workspace_bytes(int32_t K, int32_t hidden) {
+  if (K < 1 || hidden < 1) return -1;
+  const int kblocks = (K + 63) / 64, slices = (hidden + 127) / 128;
+  return (int64_t)kblocks * slices * gs::TC_TILE_BYTES;
+}
+
+int32_t gs_maxpool_mlp_pack(const float* Wm, int64_t ldw, int32_t K, int32_t hidden, void* workspace, void* stream) {
+  GS_REQUIRE(Wm && workspace && K >= 1 && hidden >= 1 && ldw >= hidden, "gs_maxpool_mlp_pack: bad arguments");
+  GS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 127u) == 0, "gs_maxpool_mlp_pack: workspace must be 128-byte aligned");
+  const int kblocks = (K + 63) / 64, slices = (hidden + 127) / 128;
+  gs::maxpool_pack_kernel<<<kblocks * slices, 256, 0, (cudaStream_t)stream>>>(Wm, ldw, K, hidden, kblocks,
+                                                                             (unsigned char*)workspace);
+  return gs::launch_check("maxpool_pack_kernel");
+}
+
+int32_t gs_maxpool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K, int64_t pitch, const int32_t* row_ids,
+                             int64_t row0, int64_t n_groups, int32_t k, const void* packed_weights, const float* bias,
+                             int32_t hidden, float* out, int64_t ldo, void* stream) {
+  GS_REQUIRE(n_groups >= 0 && k >= 1, "gs_maxpool_mlp_fused: bad n_groups / k");
+  if (n_groups == 0) return GS_OK;
+  GS_REQUIRE(table_bf16 && packed_weights && out, "gs_maxpool_mlp_fused: NULL pointer");
+  GS_REQUIRE(n_rows > 0 && K >= 1 && pitch >= K, "gs_maxpool_mlp_fused: bad table shape");
+  GS_REQUIRE((pitch * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(table_bf16) & 15u) == 0,
+             "gs_maxpool_mlp_fused: table rows must be 16-byte multiples and 16-byte aligned (pitch %% 8 == 0)");
+  GS_REQUIRE((reinterpret_cast<uintptr_t>(packed_weights) & 127u) == 0, "gs_maxpool_mlp_fused: packed weights misaligned");
+  if (k > 128 || (K + 63) / 64 > gs::MP_MAX_KB || hidden % 128 != 0) {
+    gs::set_error("gs_maxpool_mlp_fused: needs k <= 128, K <= %d, hidden %% 128 == 0 (k=%d K=%d hidden=%d)",
+                  gs::MP_MAX_KB * 64, k, K, hidden);
+    return GS_ERR_UNSUPPORTED;
+  }
+  GS_REQUIRE(ldo >= hidden, "gs_maxpool_mlp_fused: ldo < hidden");
+  gs::MpParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.table = (const __nv_bfloat16*)table_bf16;
+  prm.n_rows = n_rows; prm.pitch = pitch; prm.K = K; prm.kblocks = (K + 63) / 64;
+  prm.row_ids = row_ids; prm.row0 = row0; prm.n_groups = n_groups; prm.k = k; prm.G = 128 / k;
+  prm.n_tiles = (n_groups + prm.G - 1) / prm.G;
+  prm.hidden = hidden; prm.n_slices = hidden / 128;
+  prm.wimg = (const unsigned char*)packed_weights; prm.bias = bias; prm.out = out; prm.ldo = ldo;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GS_CUDA(cudaFuncSetAttribute(gs::maxpool_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gs::MP_SMEM));
+    attr_set = true;
+  }
+  int64_t ctas = (int64_t)(gs::sm_count() / prm.n_slices) * prm.n_slices;   // a whole number of slice groups
+  if (ctas < prm.n_slices) ctas = prm.n_slices;
+  if (ctas > prm.n_tiles * prm.n_slices) ctas = prm.n_tiles * prm.n_slices;
+  gs::maxpool_mlp_kernel<<<(unsigned)ctas, gs::MP_THREADS, gs::MP_SMEM, (cudaStream_t)stream>>>(prm);
+  return gs::launch_check("maxpool_mlp_kernel");
+}
+
+}  // extern "C"

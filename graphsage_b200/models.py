@@ -56,12 +56,13 @@ class SampleAndAggregate(object):
             return
         if not torch.is_tensor(features):
             features = torch.as_tensor(features, dtype=torch.float32)
-        features = features.to(device=device, dtype=torch.float32)
+        dt = torch.bfloat16 if features.dtype == torch.bfloat16 else torch.float32   # bf16 tables are kept (config 3)
+        features = features.to(device=device, dtype=dt)
         F_ = features.shape[1]
-        if features.stride(1) != 1 or features.stride(0) % 4 != 0 or features.data_ptr() % 16 != 0 \
+        if features.stride(1) != 1 or features.stride(0) % 8 != 0 or features.data_ptr() % 16 != 0 \
                 or features.stride(0) < ops.pad_cols(F_):
             # re-pitch once so rows are 16-byte multiples (TMA bulk copies / 128-bit loads); keep the [N+1, F] view
-            table = torch.zeros((features.shape[0], ops.pad_cols(F_)), dtype=torch.float32, device=features.device)
+            table = torch.zeros((features.shape[0], ops.pad_cols(F_)), dtype=dt, device=features.device)
             table[:, :F_] = features
             features = table[:, :F_]
         self.features = features

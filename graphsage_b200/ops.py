@@ -297,6 +297,44 @@ def sage_layer_small(src, seg, parts, combine=COMBINE_ADD, include_self=False, b
     return out
 
 
+class PackedMlpWeights(object):
+    """bf16 tile images of the max-pool MLP weight for gs_maxpool_mlp_fused, re-packed when the weight changes."""
+
+    def __init__(self):
+        self.key, self.ws = None, None
+
+    def get(self, W):
+        key = (W.data_ptr(), W._version, tuple(W.shape))
+        if key != self.key:
+            K, hidden = W.shape
+            nbytes = lib().gs_maxpool_mlp_workspace_bytes(K, hidden)
+            self.ws = torch.empty((nbytes,), dtype=torch.uint8, device=W.device)
+            Wc = W.contiguous()
+            check(lib().gs_maxpool_mlp_pack(ptr(Wc), Wc.stride(0), K, hidden, ptr(self.ws), stream_ptr()))
+            _launched(1)
+            self.key = key
+        return self.ws
+
+
+def maxpool_mlp_fused(table, n_groups, k, W, bias, packed, row_ids=None, row0=0, K=None):
+    """out[g, :] = max_j relu(table[row(g, j), :K] @ W + bias) in one tcgen05 kernel (bf16 operands, fp32 accumulate).
+    table: bfloat16 [rows, >=K] row-major with pitch % 8 == 0; W: float32 [K, hidden] (hidden % 128 == 0)."""
+    require_cuda(table, W, bias, row_ids)
+    if table.dtype != torch.bfloat16 or table.stride(1) != 1:
+        raise TypeError("table must be row-major bfloat16")
+    K = W.shape[0] if K is None else K
+    hidden = W.shape[1]
+    out = torch.empty((n_groups, hidden), dtype=torch.float32, device=table.device)
+    ws = packed.get(W)
+    if row_ids is not None:
+        row_ids = _i32(row_ids.reshape(-1), "row_ids")
+    ev = _probe("maxpool_mlp/%d" % n_groups)
+    check(lib().gs_maxpool_mlp_fused(ptr(table), table.shape[0], K, table.stride(0), ptr(row_ids), row0, n_groups, k,
+                                     ptr(ws), ptr(bias), hidden, ptr(out), out.stride(0), stream_ptr()))
+    _launched(1 if n_groups else 0, ev)
+    return out
+
+
 def l2_normalize_rows_(x):
     """In-place tf.nn.l2_normalize(x, 1) - reference graphsage/models.py:368."""
     require_cuda(x)

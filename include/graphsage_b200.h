@@ -213,6 +213,24 @@ int32_t gs_sage_layer_small(const float* src, int64_t n_src_rows, int32_t F, int
                             float* out, int64_t ldo, uint64_t* counter_dev, uint64_t counter_inc,
                             void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * K4 - the max-pool aggregator's neighbour branch fused end to end on tcgen05 (bf16 operands, fp32
+ * accumulate):   out[g, h] = max_{j<k} relu( table[row(g,j), 0:K] . Wm[0:K, h] + bm[h] )
+ *   reference graphsage/aggregators.py:176-182 (reshape -> Dense(relu,bias) -> reshape -> reduce_max),
+ *   graphsage/layers.py:104-116, with the gather of graphsage/models.py:299 fused in front.
+ *   row(g, j) = row_ids ? row_ids[g*k + j] : row0 + g*k + j;  table is bf16 [n_rows, pitch] (pitch % 8 == 0).
+ *   packed_weights: gs_maxpool_mlp_pack(Wm fp32 [K, hidden] row-major) into gs_maxpool_mlp_workspace_bytes
+ *   bytes (do it once per weight update).  Limits: K <= 640, k <= 128, hidden % 128 == 0 (else
+ *   GS_ERR_UNSUPPORTED: use gs_gather_rows + gs_sage_gemm + gs_segment_max).
+ * --------------------------------------------------------------------------------------------- */
+int64_t gs_maxpool_mlp_workspace_bytes(int32_t K, int32_t hidden);
+int32_t gs_maxpool_mlp_pack(const float* Wm, int64_t ldw, int32_t K, int32_t hidden, void* workspace,
+                            void* stream);
+int32_t gs_maxpool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K, int64_t pitch,
+                             const int32_t* row_ids, int64_t row0, int64_t n_groups, int32_t k,
+                             const void* packed_weights, const float* bias, int32_t hidden,
+                             float* out, int64_t ldo, void* stream);
+
 /* tf.nn.l2_normalize(x, 1)   reference graphsage/models.py:368-370, supervised_models.py:85 */
 int32_t gs_l2_normalize_rows(float* x, int64_t n, int32_t C, int64_t ldx, void* stream);
 

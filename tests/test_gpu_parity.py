@@ -454,3 +454,61 @@ def test_packed_weights_follow_weight_updates(gs):
         assert float(agg((x, nb))[:, 32:].abs().max()) == 0.0
     finally:
         gs.set_default_math("fp32")
+
+
+# ---------------------------------------------------------------- K4: fused max-pool MLP (bf16 tcgen05)
+@pytest.mark.parametrize("case", [
+    # (n_groups, k, K, hidden, use_ids)
+    (5120, 25, 602, 512, True),        # bench shape, hop 2 of layer 0 (one 10th of it)
+    (517, 10, 602, 512, True),         # ragged group count, 12 groups per tile
+    (301, 10, 256, 512, False),        # layer 1: dense row ranges, 4 K-blocks
+    (40, 7, 50, 128, True),            # small K (one partial K-block), one hidden slice
+    (3, 128, 64, 256, True),           # one group per tile
+    (1000, 1, 602, 1024, True),        # k = 1 (max over a single row), "big" hidden
+])
+def test_maxpool_mlp_fused_vs_reference(gs, case):
+    n_groups, k, K, hidden, use_ids = case
+    rs = np.random.RandomState(n_groups + k)
+    n_rows = 4000
+    P = gs.ops.pad_cols(K)
+    table = torch.zeros((n_rows, P), dtype=torch.bfloat16, device="cuda")
+    table[:, :K] = dev(rs.randn(n_rows, K).astype(np.float32)).to(torch.bfloat16)
+    if P > K:
+        table[:, K:] = 3.0                                      # pad columns must not leak into the result
+    W = dev((rs.randn(K, hidden) / np.sqrt(K)).astype(np.float32))
+    bias = dev(rs.randn(hidden).astype(np.float32))
+    packed = gs.ops.PackedMlpWeights()
+    if use_ids:
+        ids = rs.randint(0, n_rows, size=n_groups * k).astype(np.int32)
+        out = gs.ops.maxpool_mlp_fused(table[:, :K], n_groups, k, W, bias, packed, row_ids=dev(ids))
+        rows = table[dev(ids).long(), :K].float()
+    else:
+        row0 = 100
+        out = gs.ops.maxpool_mlp_fused(table[:, :K], n_groups, k, W, bias, packed, row0=row0)
+        rows = table[row0:row0 + n_groups * k, :K].float()
+    torch.cuda.synchronize()
+    h = torch.relu(rows.double() @ W.to(torch.bfloat16).double() + bias.double())
+    ref = h.reshape(n_groups, k, hidden).max(dim=1).values
+    assert tuple(out.shape) == (n_groups, hidden)
+    assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < 2e-5     # same bf16 operands, fp32 accumulate
+
+
+def test_maxpool_bf16_model_matches_fp32_model(gs):
+    """config 3 (bf16 max-pool path through K4) vs the fp32 generic path on the same weights: bf16-level agreement."""
+    g = load_golden("khop")
+    rs = np.random.RandomState(3)
+    n, f, B = 300, 602, 64
+    adj = g["adj"][:, :32]
+    feats = np.vstack([rs.randn(n, f).astype(np.float32), np.zeros((1, f), np.float32)])
+    seeds = rs.randint(0, n, size=B).astype(np.int32)
+    outs = {}
+    for math, table in (("fp32", dev(feats)), ("bf16", dev(feats).to(torch.bfloat16))):
+        gs.set_default_math(math)
+        gs.inits.manual_seed(11)
+        sampler = gs.UniformNeighborSampler(dev(adj), seed=5)
+        infos = [gs.SAGEInfo("node", sampler, 25, 128), gs.SAGEInfo("node", sampler, 10, 128)]
+        m = gs.SampleAndAggregate({"batch_size": B, "dropout": 0.}, table, dev(adj), None, infos, concat=True,
+                                  aggregator_type="maxpool")
+        outs[math] = m.forward(dev(seeds), normalize=True).cpu().numpy()
+    gs.set_default_math("fp32")
+    assert rel_err(outs["bf16"], outs["fp32"]) < 3e-2

@@ -1,0 +1,30 @@
+"""K4 micro-benchmark at the Reddit shape: hop-2 of layer 0 (128000 gathered rows x 602 -> 512, max over 25)."""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import graphsage_b200 as gs
+from graphsage_b200 import ops
+dev = torch.device("cuda")
+N, F, H, B = 232965, 602, 512, 512
+P = ops.pad_cols(F)
+table = torch.zeros((N + 1, P), dtype=torch.bfloat16, device=dev)
+table[:N, :F] = torch.randn((N, F), device=dev).to(torch.bfloat16)
+W = torch.randn(F, H, device=dev) / 25.0
+bias = torch.randn(H, device=dev)
+packed = ops.PackedMlpWeights()
+rs = np.random.RandomState(0)
+sets = [torch.from_numpy(rs.randint(0, N, size=B * 250).astype(np.int32)).to(dev) for _ in range(12)]
+for i in range(3):
+    ops.maxpool_mlp_fused(table[:, :F], B * 10, 25, W, bias, packed, row_ids=sets[i])
+torch.cuda.synchronize()
+torch.cuda._sleep(4000000)
+evs = []
+for i in range(3, 12):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); ops.maxpool_mlp_fused(table[:, :F], B * 10, 25, W, bias, packed, row_ids=sets[i]); e1.record()
+    evs.append((e0, e1))
+torch.cuda.synchronize()
+t = np.median([a.elapsed_time(b) for a, b in evs])
+flops = 2.0 * B * 250 * F * H
+print("maxpool_mlp_fused hop2: %.1f us  %.1f TFLOP/s (algorithmic, K=602)  gathered %.1f GB/s" % (
+    t * 1e3, flops / t / 1e9, B * 250 * F * 2 / t / 1e6))
