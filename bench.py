@@ -108,6 +108,11 @@ def make_weights(kind, rs):
                 dict(neigh_weights=glorot(2 * DIM, DIM), self_weights=glorot(2 * DIM, DIM))]
     if kind == "gcn":
         return [dict(weights=glorot(F, 2 * DIM)), dict(weights=glorot(2 * DIM, 2 * DIM))]
+    if kind == "maxpool":     # hidden 512 ("small"), reference graphsage/aggregators.py:139-142
+        return [dict(mlp_weights=glorot(F, 512), mlp_bias=np.zeros(512, np.float32), neigh_weights=glorot(512, DIM),
+                     self_weights=glorot(F, DIM)),
+                dict(mlp_weights=glorot(2 * DIM, 512), mlp_bias=np.zeros(512, np.float32), neigh_weights=glorot(512, DIM),
+                     self_weights=glorot(2 * DIM, DIM))]
     raise ValueError(kind)
 
 
@@ -117,7 +122,7 @@ def cpu_reference_rate(g, kind, weights, n_batches, warm, seed_rs, budget_s=None
     from oracle import torch_ref
     adj_t, feats_t = torch.from_numpy(g["adj"]), torch.from_numpy(g["features"])
     aggs = [{k: torch.from_numpy(v) for k, v in w.items()} for w in weights]
-    concat = kind == "mean"
+    concat = kind != "gcn"
     # use the thread count that is fastest on this host (all cores is often slower for the gather)
     ncpu = len(os.sched_getaffinity(0))
     best = (None, 1e30)
@@ -152,7 +157,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--aggregator", default="mean", choices=["mean", "gcn"])
+    ap.add_argument("--aggregator", default="mean", choices=["mean", "gcn", "maxpool"],
+                    help="mean = BASELINE configs[1] (default); maxpool (+ bf16 features, --math bf16) = configs[2]")
     ap.add_argument("--math", default=os.environ.get("GS_MATH", "tf32x3"),
                     help="tf32x3 (tcgen05, fp32-grade: meets the 1e-4 parity bar) | fp32 (CUDA cores) | tf32 | bf16")
     ap.add_argument("--cpu-batches", type=int, default=12)
@@ -162,6 +168,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     kind = args.aggregator
+    if kind == "maxpool":
+        args.math = "bf16"            # config 3: bf16 features / weights, fp32 accumulate, K4 on tcgen05
     workload = "reddit-shape synthetic N=%d F=%d max_degree=%d graphsage_%s 2-hop fanout 25x10 batch=%d dims=[%d,%d,%d]" % (
         N_NODES, F, MAX_DEG, kind, BATCH, F, DIM, DIM)
 
@@ -198,15 +206,16 @@ def main():
 
     g = build_graph(rank, world, (lambda: dist.barrier()) if dist is not None else None)
     dev = torch.device("cuda", local_rank)
-    table = torch.zeros((N_NODES + 1, ops.pad_cols(F)), dtype=torch.float32, device=dev)
-    table[:, :F] = torch.from_numpy(g["features"]).to(dev)
+    tdtype = torch.bfloat16 if kind == "maxpool" else torch.float32
+    table = torch.zeros((N_NODES + 1, ops.pad_cols(F)), dtype=tdtype, device=dev)
+    table[:, :F] = torch.from_numpy(g["features"]).to(dev).to(tdtype)
     adj_dev = torch.from_numpy(g["adj"]).to(dev)
     gs.set_default_math(args.math)
     sampler = gs.UniformNeighborSampler(adj_dev, seed=123)
-    dims = (DIM, DIM) if kind == "mean" else (2 * DIM, 2 * DIM)
+    dims = (2 * DIM, 2 * DIM) if kind == "gcn" else (DIM, DIM)
     infos = [gs.SAGEInfo("node", sampler, FANOUT[0], dims[0]), gs.SAGEInfo("node", sampler, FANOUT[1], dims[1])]
     model = gs.SampleAndAggregate({"batch_size": BATCH, "dropout": 0.}, table[:, :F], adj_dev, None, infos,
-                                  concat=(kind == "mean"), aggregator_type=kind, device=dev)
+                                  concat=(kind != "gcn"), aggregator_type=kind, device=dev)
     weights = make_weights(kind, np.random.RandomState(7))
 
     def barrier():
@@ -222,7 +231,7 @@ def main():
         return float(t.item())
 
     total = args.warmup + args.steps
-    probe_name = "gather_mean/%d" % (BATCH * 11)
+    probe_name = ("maxpool_mlp/%d" % (BATCH * 10)) if kind == "maxpool" else ("gather_mean/%d" % (BATCH * 11))
 
     def measure(mdl, lo, hi, tag):
         """value (ids resident in HBM) and e2e (pinned-host ids in, result to pinned host) for one model."""
@@ -233,7 +242,12 @@ def main():
         mdl.forward(seeds_dev[0])                       # creates the aggregators
         for a, w in zip(mdl.aggregators, weights):
             for k_, v in w.items():
-                a.vars[k_] = torch.from_numpy(v).to(dev)
+                if k_ == "mlp_weights":
+                    a.mlp_layers[0].vars["weights"] = torch.from_numpy(v).to(dev)
+                elif k_ == "mlp_bias":
+                    a.mlp_layers[0].vars["bias"] = torch.from_numpy(v).to(dev)
+                else:
+                    a.vars[k_] = torch.from_numpy(v).to(dev)
         runner = mdl.graphed(BATCH, normalize=True, probe=probe_name)     # CUDA-graph replay of forward()
         for i in range(args.warmup):
             runner(seeds_dev[i])
@@ -276,7 +290,7 @@ def main():
 
     # node-partitioned table with the halo exchange fused into the gather (peer loads over NVLink); owner-computes seeds
     part = None
-    if world > 1 and not args.no_partitioned:
+    if world > 1 and not args.no_partitioned and kind != "maxpool":
         from graphsage_b200 import parallel
         R = parallel.rows_per_shard(N_NODES, world)
         lo, hi = rank * R, min(N_NODES, (rank + 1) * R)
@@ -284,7 +298,7 @@ def main():
         sampler_p = gs.UniformNeighborSampler(adj_dev, seed=123)
         infos_p = [gs.SAGEInfo("node", sampler_p, FANOUT[0], dims[0]), gs.SAGEInfo("node", sampler_p, FANOUT[1], dims[1])]
         model_p = gs.SampleAndAggregate({"batch_size": BATCH, "dropout": 0.}, shard, adj_dev, None, infos_p,
-                                        concat=(kind == "mean"), aggregator_type=kind, device=dev)
+                                        concat=(kind != "gcn"), aggregator_type=kind, device=dev)
         pr = measure(model_p, lo, hi, "partitioned")
         rs = np.random.RandomState(1000 + rank)
         smp, _ = model_p.sample(torch.from_numpy(rs.randint(lo, hi, size=BATCH).astype(np.int32)).to(dev), infos_p)
@@ -302,7 +316,19 @@ def main():
     # ---- roofline of the dominant kernel: the layer-0 fused gather+mean
     peak, peak_src = peaks()
     roof = None
-    if rep["gather_kernel_ms"] > 0:
+    if kind == "maxpool" and rep["gather_kernel_ms"] > 0:
+        avg_ms = rep["gather_kernel_ms"]
+        flops = 2.0 * BATCH * 250 * F * 512                       # hop-2 MLP: [128000, 602] x [602, 512]
+        tpeak = 1444.6
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            tpeak = float(json.load(open(pk)).get("bf16_tflops_sustained", tpeak))
+        ach = flops / (avg_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "maxpool_mlp_kernel (layer 0, hop 2: gather + MLP + ReLU + max over 25)",
+                "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None,
+                "peak_source": "measured sustained cuBLAS bf16 (MEASURED_PEAKS.json)", "avg_kernel_ms": avg_ms,
+                "algorithmic_flops_per_launch": flops, "kernel_share_of_step": avg_ms / (ms_total / args.steps)}
+    elif rep["gather_kernel_ms"] > 0:
         avg_ms = rep["gather_kernel_ms"]
         achieved = GATHER_BYTES / (avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "gather_mean (layer 0, hops 0+1)", "achieved": achieved, "peak": peak,
@@ -319,7 +345,7 @@ def main():
     print(json.dumps({
         "metric": "seed_nodes_per_sec", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "bf16" if kind == "maxpool" else "f32", "data": "synthetic",
         "config": {"workload": workload, "math": args.math, "parallelism": "replicated-table dp%d" % world,
                    "l2": "inputs larger than L2 (567 MB feature table vs 126 MB L2; fresh random seeds every step)"},
         "e2e": {"value": e2e_value, "unit": "nodes/s", "h2d_bytes_per_step": BATCH * 4,

@@ -8,7 +8,10 @@
 // Wm^T (<= 10 K-blocks x 16 KB, pre-swizzled bf16 tile images) is bulk-copied into shared memory ONCE and stays
 // resident.  The CTA then walks M tiles (G = floor(128 / k) whole fanout groups per tile, zero rows after them):
 //   warps 0-3  gather-A producers: cp.async 16-byte pieces of the addressed table rows straight into the UMMA
-//              K-major SWIZZLE_128B tile (bf16 in the table = bf16 in the tile: no conversion), 2 K-blocks ahead
+//              K-major SWIZZLE_128B tile (bf16 in the table = bf16 in the tile: no conversion), 2 K-blocks ahead.
+//              (Measured alternatives - 3-5 K-blocks of 128-bit register loads per thread, with 4 or 8 producer
+//              warps, and an L2 prefetch of the next tile - were slower; the limiter is shared-memory capacity:
+//              the 160 KB resident weight slice leaves 48 KB for A stages.  See DESIGN.md section 4.)
 //   warp  4    MMA issuer: tcgen05.mma.kind::f16 (M128 N128 K16), accumulators double-buffered in TMEM
 //   warp  5    loads the resident weight slice (cp.async.bulk + mbarrier)
 //   warps 6-9  epilogue: tcgen05.ld -> + bias -> ReLU -> staged transpose in shared memory -> max over the k rows
@@ -19,7 +22,8 @@ namespace gs {
 
 constexpr int MP_SA = 3;                      // A stages (16 KB each)
 constexpr int MP_MAX_KB = 10;                 // resident weight K-blocks (K <= 640)
-constexpr int MP_THREADS = 320;
+constexpr int MP_PROD_WARPS = 4;               // gather-A producer warps
+constexpr int MP_THREADS = (MP_PROD_WARPS + 6) * 32;
 constexpr int MP_STAGE_LD = 129;              // padded row length of the epilogue staging [32][129]
 constexpr int MP_SMEM = MP_MAX_KB * TC_TILE_BYTES + MP_SA * TC_TILE_BYTES + 32 * MP_STAGE_LD * 4 + 1024;
 
@@ -35,6 +39,7 @@ struct MpParams {
   int32_t hidden, n_slices;
   const unsigned char* wimg;    // packed Wm^T: [n_slices][kblocks][16 KB]
   const float* bias;            // [hidden] or NULL
+  int32_t prefetch;             // L2-prefetch the next tile's rows
   float* out;                   // [n_groups, hidden]
   int64_t ldo;
 };
@@ -58,10 +63,21 @@ __global__ void __launch_bounds__(256) maxpool_pack_kernel(const float* __restri
   }
 }
 
+// timeline probe (CTA 0): globaltimer stamps, 8 slots per tile for the first 12 tiles
+__device__ unsigned long long g_mp_dbg[128];
+__device__ __forceinline__ void mp_stamp(uint32_t tcount, int slot) {
+  if (blockIdx.x == 0 && tcount < 12) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_mp_dbg[tcount * 8 + slot] = t;
+  }
+}
+
 __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid_constant__ MpParams prm) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_a[MP_SA], empty_a[MP_SA], acc_full[2], acc_empty[2], b_full;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float bias_s[128];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* b_res = smem;                                        // resident weight slice
   unsigned char* a_ring = smem + MP_MAX_KB * TC_TILE_BYTES;
@@ -74,7 +90,7 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < MP_SA; ++s) {
-      mbar_init(&full_a[s], 4);           // one arrive per producer warp
+      mbar_init(&full_a[s], MP_PROD_WARPS);   // one arrive per producer warp
       mbar_init(&empty_a[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -84,7 +100,7 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
     mbar_init(&b_full, 1);
     fence_mbar_init();
   }
-  if (warp == 4) {
+  if (warp == MP_PROD_WARPS) {
     tmem_alloc(&tmem_base_smem, 256);     // two 128-column fp32 accumulators
     tmem_relinquish();
   }
@@ -93,7 +109,7 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
-  if (warp < 4) {
+  if (warp < MP_PROD_WARPS) {
     // =============================== gather-A producers ===============================
     const int tid = threadIdx.x;                    // 0..127
     const int c = tid & 7, r0 = tid >> 3;           // chunk column, first row; rows r0 + 16 i
@@ -107,7 +123,9 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_a[s]);
     };
-    for (int64_t t = tile0; t < prm.n_tiles; t += tile_step) {
+    uint32_t ptile = 0;
+    for (int64_t t = tile0; t < prm.n_tiles; t += tile_step, ++ptile) {
+      if (threadIdx.x == 0) mp_stamp(ptile, 0);
       const __nv_bfloat16* rowp[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -140,19 +158,22 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
           --pending;
         }
       }
+      if (threadIdx.x == 0) mp_stamp(ptile, 1);
     }
     // drain
     if (pending == 2) { cp_async_wait<1>(); publish(it - 2); --pending; }
     if (pending == 1) { cp_async_wait<0>(); publish(it - 1); --pending; }
-  } else if (warp == 4) {
+  } else if (warp == MP_PROD_WARPS) {
     // =============================== MMA issuer ===============================
     constexpr uint32_t idesc = make_idesc(1u, TC_BM, TC_BN);          // bf16 x bf16 -> fp32
     mbar_wait(&b_full, 0);
     uint32_t it = 0, tcount = 0;
     for (int64_t t = tile0; t < prm.n_tiles; t += tile_step, ++tcount) {
       const uint32_t buf = tcount & 1u;
+      if (lane == 0) mp_stamp(tcount, 2);
       mbar_wait(&acc_empty[buf], ((tcount >> 1) & 1u) ^ 1u);          // epilogue has drained this accumulator
       tc_fence_after();
+      if (lane == 0) mp_stamp(tcount, 3);
       const uint32_t tmem_acc = tmem_base + buf * 128u;
       for (int kb = 0; kb < kblocks; ++kb, ++it) {
         const int s = it % MP_SA;
@@ -166,11 +187,12 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
             umma_ss<true>(tmem_acc, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), idesc, (kb > 0 || k4 > 0) ? 1u : 0u);
           umma_commit(&empty_a[s]);
           if (kb == kblocks - 1) umma_commit(&acc_full[buf]);
+          if (kb == kblocks - 1) mp_stamp(tcount, 4);
         }
         __syncwarp();
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == MP_PROD_WARPS + 1) {
     // =============================== resident weight slice ===============================
     if (lane == 0) {
       mbar_expect_tx(&b_full, (uint32_t)(kblocks * TC_TILE_BYTES));
@@ -181,15 +203,19 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
     __syncwarp();
   } else {
     // =============================== epilogue ===============================
-    const int et = threadIdx.x - 192;               // 0..127
-    const int q = warp & 3;                         // TMEM lane quarter of this warp (warps 6,7,8,9 -> 2,3,0,1)
+    const int et = threadIdx.x - (MP_PROD_WARPS + 2) * 32;   // 0..127
+    const int q = warp & 3;                         // TMEM lane quarter of this warp (four consecutive warps cover 0..3)
     const int row = q * 32 + lane;                  // tile row held by this thread
     const int k = prm.k, G = prm.G;
+    bias_s[et] = prm.bias ? prm.bias[slice * 128 + et] : 0.f;     // this CTA's 128 bias values, once
+    named_bar_sync(1, 128);
     uint32_t tcount = 0;
     for (int64_t t = tile0; t < prm.n_tiles; t += tile_step, ++tcount) {
       const uint32_t buf = tcount & 1u;
+      if (et == 0) mp_stamp(tcount, 5);
       mbar_wait(&acc_full[buf], (tcount >> 1) & 1u);
       tc_fence_after();
+      if (et == 0) mp_stamp(tcount, 6);
       const uint32_t tmem_acc = tmem_base + buf * 128u + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int cb = 0; cb < 4; ++cb) {
@@ -197,22 +223,30 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
         tmem_ld_32x32(tmem_acc + (uint32_t)(cb * 32), r);
         tmem_ld_wait();
         const int hcol0 = slice * 128 + cb * 32;
+        // raw accumulators go to the staging tile; bias and ReLU are applied AFTER the max
+        // (max_j relu(x_j + b) == relu(max_j x_j + b): b is per column, relu is monotone)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float v = __uint_as_float(r[j]);
-          if (prm.bias) v += prm.bias[hcol0 + j];
-          stage[j * MP_STAGE_LD + row] = fmaxf(v, 0.f);               // ReLU (Dense act, aggregators.py:147)
-        }
+        for (int j = 0; j < 32; ++j) stage[j * MP_STAGE_LD + row] = __uint_as_float(r[j]);
         named_bar_sync(1, 128);
-        // (column cc, group g) work items: max over the group's k consecutive rows
-        for (int w = et; w < 32 * G; w += 128) {
-          const int cc = w & 31, g = w >> 5;
-          const int64_t gg = t * G + g;
-          if (gg < prm.n_groups) {
-            const float* p = stage + cc * MP_STAGE_LD + g * k;
-            float m = p[0];
-            for (int j = 1; j < k; ++j) m = fmaxf(m, p[j]);
-            prm.out[gg * prm.ldo + hcol0 + cc] = m;
+        // thread = (column cc, group residue): max over each group's k consecutive rows, 8 independent
+        // shared loads per batch
+        {
+          const int cc = et & 31;
+          for (int g = et >> 5; g < G; g += 4) {
+            const int64_t gg = t * G + g;
+            if (gg < prm.n_groups) {
+              const float* p = stage + cc * MP_STAGE_LD + g * k;
+              float m = -3.0e38f;
+              int j = 0;
+              for (; j + 8 <= k; j += 8) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = p[j + u];
+                m = fmaxf(m, fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7]))));
+              }
+              for (; j < k; ++j) m = fmaxf(m, p[j]);
+              prm.out[gg * prm.ldo + hcol0 + cc] = fmaxf(m + bias_s[cb * 32 + cc], 0.f);   // Dense bias + ReLU
+            }
           }
         }
         named_bar_sync(1, 128);
@@ -220,10 +254,11 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (et == 0) mp_stamp(tcount, 7);
     }
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == MP_PROD_WARPS) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
@@ -232,6 +267,14 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
 }  // namespace gs
 
 extern "C" {
+
+/* developer probe (not in the public header) */
+int32_t gs_debug_read_maxpool_timeline(unsigned long long* out_host, int32_t n) {
+  if (n > 128) n = 128;
+  GS_CUDA(cudaDeviceSynchronize());
+  GS_CUDA(cudaMemcpyFromSymbol(out_host, gs::g_mp_dbg, sizeof(unsigned long long) * n));
+  return GS_OK;
+}
 
 int64_t gs_maxpool_mlp_workspace_bytes(int32_t K, int32_t hidden) {
   if (K < 1 || hidden < 1) return -1;
@@ -272,6 +315,7 @@ int32_t gs_maxpool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K, 
   prm.n_tiles = (n_groups + prm.G - 1) / prm.G;
   prm.hidden = hidden; prm.n_slices = hidden / 128;
   prm.wimg = (const unsigned char*)packed_weights; prm.bias = bias; prm.out = out; prm.ldo = ldo;
+  prm.prefetch = gs::tuning("maxpool_prefetch", 1);
   static bool attr_set = false;
   if (!attr_set) {
     GS_CUDA(cudaFuncSetAttribute(gs::maxpool_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gs::MP_SMEM));

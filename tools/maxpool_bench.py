@@ -6,7 +6,7 @@ import graphsage_b200 as gs
 from graphsage_b200 import ops
 dev = torch.device("cuda")
 N, F, H, B = 232965, 602, 512, 512
-P = ops.pad_cols(F)
+P = int(os.environ.get('MP_PITCH', ops.pad_cols(F)))
 table = torch.zeros((N + 1, P), dtype=torch.bfloat16, device=dev)
 table[:N, :F] = torch.randn((N, F), device=dev).to(torch.bfloat16)
 W = torch.randn(F, H, device=dev) / 25.0
@@ -28,3 +28,13 @@ t = np.median([a.elapsed_time(b) for a, b in evs])
 flops = 2.0 * B * 250 * F * H
 print("maxpool_mlp_fused hop2: %.1f us  %.1f TFLOP/s (algorithmic, K=602)  gathered %.1f GB/s" % (
     t * 1e3, flops / t / 1e9, B * 250 * F * 2 / t / 1e6))
+import ctypes
+buf = (ctypes.c_ulonglong * 128)()
+gs._lib.lib().gs_debug_read_maxpool_timeline(buf, 128)
+t0 = buf[0]
+names = ["prod: tile start", "prod: tile issued", "mma: want acc", "mma: got acc", "mma: last issued", "epi: want acc", "epi: got acc", "epi: done"]
+for tc in range(3, 7):
+    print("tile %d: " % tc + "  ".join("%s=%.2f" % (names[j].split(": ")[1][:11] + "@" + names[j][:3], (buf[tc * 8 + j] - t0) / 1e3) for j in range(8)))
+
+n = max(1, buf[104])
+print("producer step cycles (avg over %d K-blocks): wait %.0f  stores %.0f  fence %.0f  arrive %.0f" % (n, buf[100]/n, buf[101]/n, buf[102]/n, buf[103]/n))
