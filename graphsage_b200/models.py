@@ -169,6 +169,10 @@ class SampleAndAggregate(object):
         """CUDA-graph runner of forward() for a fixed batch size (see GraphedForward)."""
         return GraphedForward(self, batch_size, normalize, probe)
 
+    def pipelined(self, batch_size, normalize=True, depth=2):
+        """Host-buffer, copy/compute-overlapped front end (see PipelinedForward)."""
+        return PipelinedForward(self, batch_size, normalize, depth)
+
     def forward(self, batch, normalize=True):
         """sample -> aggregate -> l2_normalize (reference models.py:347-350, 368) for one id batch."""
         batch = batch.to(device=self.device, dtype=torch.int32).reshape(-1)
@@ -196,11 +200,14 @@ class GraphedForward(object):
     bench.py can bracket it with CUDA events inside the timed region.
     """
 
-    def __init__(self, model, batch_size, normalize=True, probe=None):
+    def __init__(self, model, batch_size, normalize=True, probe=None, first_step=0, step_stride=1):
+        """first_step / step_stride: this runner replays eager steps first_step, first_step + step_stride, ...
+        (several runners can interleave - PipelinedForward uses two - and still reproduce the eager RNG sequence)."""
         self.model, self.batch_size, self.normalize = model, int(batch_size), normalize
         dev = model.device
         self.ids = torch.zeros(self.batch_size, dtype=torch.int32, device=dev)
-        self.counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.first_step, self.step_stride = int(first_step), int(step_stride)
+        self.counter = torch.full((1,), len(model.layer_infos) * self.first_step, dtype=torch.int64, device=dev)
         samplers = []
         for info in model.layer_infos:
             if all(info.neigh_sampler is not s for s in samplers):
@@ -234,7 +241,7 @@ class GraphedForward(object):
             ops.STAGE_HOOK = hook
             try:
                 launches0 = ops.LAUNCHES
-                model._graph_bump = (self.counter, self.n_calls)   # the step advances the device RNG counter itself
+                model._graph_bump = (self.counter, self.n_calls * self.step_stride)   # the step advances the device RNG counter
                 try:
                     self.out = model.forward(self.ids, normalize)
                 finally:
@@ -247,14 +254,16 @@ class GraphedForward(object):
             self._reset_python_counters()
         torch.cuda.current_stream(dev).wait_stream(self.stream)
         self.replays = 0
+        # the warm-up forwards and the capture pass advanced the device counter through the fused bump; rewind
+        self.counter.fill_(self.n_calls * self.first_step)
 
     def _reset_python_counters(self):
         for s, c in zip(self.samplers, self.base_counters):
             s.counter = c
 
     def reset(self, replays=0):
-        """Next replay behaves like eager forward number `replays` since construction."""
-        self.counter.fill_(self.n_calls * replays)
+        """Next replay behaves like this runner's replay number `replays` (eager step first_step + replays*step_stride)."""
+        self.counter.fill_(self.n_calls * (self.first_step + replays * self.step_stride))
         self.replays = replays
 
     def __call__(self, ids=None, probe_events=None):
@@ -273,3 +282,51 @@ class GraphedForward(object):
     def close(self):
         for s in self.samplers:
             s.counter_dev = None
+
+
+class PipelinedForward(object):
+    """Host-buffer front end of the hot path: ids come from (pinned) host memory, the result lands in (pinned) host
+    memory, and consecutive steps overlap - two CUDA-graph runners alternate on the compute stream while a copy
+    stream drains the previous step's result, so the device->host transfer hides behind the next step's kernels.
+    Step i reproduces eager forward number i (same RNG counters).
+
+        pipe = model.pipelined(batch_size)
+        for i in range(n): pipe.submit(ids_host[i], out_host[i])
+        pipe.synchronize()
+    """
+
+    def __init__(self, model, batch_size, normalize=True, depth=2):
+        dev = model.device
+        self.model, self.depth = model, int(depth)
+        self.runners = [GraphedForward(model, batch_size, normalize, first_step=r, step_stride=self.depth)
+                        for r in range(self.depth)]
+        self.compute = torch.cuda.Stream(device=dev)
+        self.copy = torch.cuda.Stream(device=dev)
+        self.done = [torch.cuda.Event() for _ in range(self.depth)]
+        self.drained = [torch.cuda.Event() for _ in range(self.depth)]
+        self.step = 0
+        self.compute.wait_stream(torch.cuda.current_stream(dev))
+        for e in self.drained:
+            e.record(self.compute)
+
+    def submit(self, ids_host, out_host):
+        r = self.step % self.depth
+        run = self.runners[r]
+        with torch.cuda.stream(self.compute):
+            self.compute.wait_event(self.drained[r])          # this runner's previous result has left the device
+            out = run(ids_host)                               # async H2D of the ids + graph replay
+            self.done[r].record(self.compute)
+        with torch.cuda.stream(self.copy):
+            self.copy.wait_event(self.done[r])
+            out_host.copy_(out, non_blocking=True)
+            self.drained[r].record(self.copy)
+        self.step += 1
+
+    def synchronize(self):
+        self.compute.synchronize()
+        self.copy.synchronize()
+
+    def close(self):
+        self.synchronize()
+        for run in self.runners:
+            run.close()

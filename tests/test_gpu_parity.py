@@ -512,3 +512,23 @@ def test_maxpool_bf16_model_matches_fp32_model(gs):
         outs[math] = m.forward(dev(seeds), normalize=True).cpu().numpy()
     gs.set_default_math("fp32")
     assert rel_err(outs["bf16"], outs["fp32"]) < 3e-2
+
+
+def test_pipelined_forward_matches_eager(gs):
+    g = load_golden("khop")
+    m, infos, fan, dims = _build_model(gs, g, "mean", counter=40)
+    B = len(g["seeds"])
+    rs = np.random.RandomState(4)
+    n = g["adj"].shape[0] - 1
+    batches = [rs.randint(0, n, size=B).astype(np.int32) for _ in range(5)]
+    eager = [m.forward(dev(b), normalize=True).clone() for b in batches]        # counters 40.. 49
+    infos[0].neigh_sampler.counter = 40
+    pipe = m.pipelined(B)
+    ids_host = [torch.from_numpy(b).pin_memory() for b in batches]
+    outs = [torch.empty((B, eager[0].shape[1]), dtype=torch.float32).pin_memory() for _ in batches]
+    for i in range(5):
+        pipe.submit(ids_host[i], outs[i])
+    pipe.synchronize()
+    for i in range(5):
+        assert torch.equal(outs[i], eager[i].cpu()), "pipelined step %d differs from eager step %d" % (i, i)
+    pipe.close()
