@@ -231,6 +231,17 @@ int32_t gs_maxpool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K, 
                              const void* packed_weights, const float* bias, int32_t hidden,
                              float* out, int64_t ldo, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * One pipelined step from HOST buffers in a single call (no per-kernel host work): on compute_stream wait
+ * until the previous result of this slot has been drained, copy the ids host->device, launch the captured
+ * CUDA graph(s) of the step; on copy_stream copy the result device->host once the step is done.
+ * All handles are the CUDA objects of the caller (cudaGraphExec_t, cudaStream_t, cudaEvent_t as void*); host
+ * buffers should be pinned.  This is the e2e entry a serving loop calls once per batch.
+ * --------------------------------------------------------------------------------------------- */
+int32_t gs_pipeline_step(const void* ids_host, void* ids_dev, int64_t ids_bytes, void* const* graph_execs_host,
+                         int32_t n_graphs, const void* out_dev, void* out_host, int64_t out_bytes,
+                         void* compute_stream, void* copy_stream, void* ev_done, void* ev_drained);
+
 /* tf.nn.l2_normalize(x, 1)   reference graphsage/models.py:368-370, supervised_models.py:85 */
 int32_t gs_l2_normalize_rows(float* x, int64_t n, int32_t C, int64_t ldx, void* stream);
 
