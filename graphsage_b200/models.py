@@ -306,7 +306,7 @@ class PipelinedForward(object):
         self.drained = [torch.cuda.Event() for _ in range(self.depth)]
         self.step = 0
         self.compute.wait_stream(torch.cuda.current_stream(dev))
-        for e in self.drained:
+        for e in self.drained + self.done:                    # also creates the underlying CUDA events
             e.record(self.compute)
 
     def _fast_handles(self):
