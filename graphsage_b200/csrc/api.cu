@@ -82,13 +82,17 @@ int32_t gs_perm_prefix_host(uint64_t seed, uint64_t counter, int32_t max_deg, in
 }
 
 int32_t gs_pipeline_step(const void* ids_host, void* ids_dev, int64_t ids_bytes, void* const* graph_execs_host,
-                         int32_t n_graphs, const void* out_dev, void* out_host, int64_t out_bytes, void* compute_stream,
-                         void* copy_stream, void* ev_done, void* ev_drained) {
-  GS_REQUIRE(ids_host && ids_dev && graph_execs_host && out_dev && out_host && ev_done && ev_drained && n_graphs >= 1,
+                         int32_t n_graphs, const void* out_dev, void* out_host, int64_t out_bytes, void* h2d_stream,
+                         void* compute_stream, void* copy_stream, void* ev_ids, void* ev_done, void* ev_drained) {
+  GS_REQUIRE(ids_host && ids_dev && graph_execs_host && out_dev && out_host && ev_ids && ev_done && ev_drained &&
+                 n_graphs >= 1,
              "gs_pipeline_step: NULL argument");
-  cudaStream_t cs = (cudaStream_t)compute_stream, ps = (cudaStream_t)copy_stream;
+  cudaStream_t hs = (cudaStream_t)h2d_stream, cs = (cudaStream_t)compute_stream, ps = (cudaStream_t)copy_stream;
+  GS_CUDA(cudaStreamWaitEvent(hs, (cudaEvent_t)ev_done, 0));
+  GS_CUDA(cudaMemcpyAsync(ids_dev, ids_host, (size_t)ids_bytes, cudaMemcpyHostToDevice, hs));
+  GS_CUDA(cudaEventRecord((cudaEvent_t)ev_ids, hs));
+  GS_CUDA(cudaStreamWaitEvent(cs, (cudaEvent_t)ev_ids, 0));
   GS_CUDA(cudaStreamWaitEvent(cs, (cudaEvent_t)ev_drained, 0));
-  GS_CUDA(cudaMemcpyAsync(ids_dev, ids_host, (size_t)ids_bytes, cudaMemcpyHostToDevice, cs));
   for (int i = 0; i < n_graphs; ++i) GS_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_execs_host[i], cs));
   GS_CUDA(cudaEventRecord((cudaEvent_t)ev_done, cs));
   GS_CUDA(cudaStreamWaitEvent(ps, (cudaEvent_t)ev_done, 0));

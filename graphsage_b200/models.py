@@ -302,11 +302,15 @@ class PipelinedForward(object):
                         for r in range(self.depth)]
         self.compute = torch.cuda.Stream(device=dev)
         self.copy = torch.cuda.Stream(device=dev)
+        self.h2d = torch.cuda.Stream(device=dev)
+        self.ids_ready = [torch.cuda.Event() for _ in range(self.depth)]
         self.done = [torch.cuda.Event() for _ in range(self.depth)]
         self.drained = [torch.cuda.Event() for _ in range(self.depth)]
         self.step = 0
+        import os
+        self.use_c_step = os.environ.get("GS_PIPELINE_PY", "0") != "1"     # GS_PIPELINE_PY=1: torch-API path (debug)
         self.compute.wait_stream(torch.cuda.current_stream(dev))
-        for e in self.drained + self.done:                    # also creates the underlying CUDA events
+        for e in self.drained + self.done + self.ids_ready:   # also creates the underlying CUDA events
             e.record(self.compute)
 
     def _fast_handles(self):
@@ -318,7 +322,8 @@ class PipelinedForward(object):
                 for r, run in enumerate(self.runners):
                     execs = (c_vp * len(run.graphs))(*[g.raw_cuda_graph_exec() for g in run.graphs])
                     hs.append((execs, len(run.graphs), run.ids.data_ptr(), run.ids.numel() * 4, run.out.data_ptr(),
-                               run.out.numel() * 4, self.done[r].cuda_event, self.drained[r].cuda_event))
+                               run.out.numel() * 4, self.ids_ready[r].cuda_event, self.done[r].cuda_event,
+                               self.drained[r].cuda_event))
                 self._handles = hs
             except Exception:
                 self._handles = False
@@ -327,13 +332,14 @@ class PipelinedForward(object):
     def submit(self, ids_host, out_host):
         r = self.step % self.depth
         run = self.runners[r]
-        hs = self._fast_handles()
+        hs = self._fast_handles() if self.use_c_step else None
         if hs and ids_host.dtype == torch.int32 and not ids_host.is_cuda and ids_host.is_contiguous() \
                 and out_host.is_contiguous() and out_host.numel() * 4 == hs[r][5]:
-            execs, n, ids_dev, ids_bytes, out_dev, out_bytes, ev_done, ev_drained = hs[r]
+            execs, n, ids_dev, ids_bytes, out_dev, out_bytes, ev_ids, ev_done, ev_drained = hs[r]
             ops.check(ops.lib().gs_pipeline_step(ids_host.data_ptr(), ids_dev, ids_bytes, execs, n, out_dev,
-                                                 out_host.data_ptr(), out_bytes, self.compute.cuda_stream,
-                                                 self.copy.cuda_stream, ev_done, ev_drained))
+                                                 out_host.data_ptr(), out_bytes, self.h2d.cuda_stream,
+                                                 self.compute.cuda_stream, self.copy.cuda_stream, ev_ids, ev_done,
+                                                 ev_drained))
             run.replays += 1
             self.step += 1
             return
@@ -348,6 +354,7 @@ class PipelinedForward(object):
         self.step += 1
 
     def synchronize(self):
+        self.h2d.synchronize()
         self.compute.synchronize()
         self.copy.synchronize()
 

@@ -232,15 +232,20 @@ int32_t gs_maxpool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K, 
                              float* out, int64_t ldo, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * One pipelined step from HOST buffers in a single call (no per-kernel host work): on compute_stream wait
- * until the previous result of this slot has been drained, copy the ids host->device, launch the captured
- * CUDA graph(s) of the step; on copy_stream copy the result device->host once the step is done.
- * All handles are the CUDA objects of the caller (cudaGraphExec_t, cudaStream_t, cudaEvent_t as void*); host
- * buffers should be pinned.  This is the e2e entry a serving loop calls once per batch.
+ * One pipelined step from HOST buffers in a single call (no per-kernel host work), on three streams:
+ *   h2d_stream     : wait ev_done (this slot's previous step no longer reads ids_dev), copy ids host->device,
+ *                    record ev_ids
+ *   compute_stream : wait ev_ids and ev_drained (this slot's previous result has left the device), launch the
+ *                    captured CUDA graph(s) of the step, record ev_done
+ *   copy_stream    : wait ev_done, copy the result device->host, record ev_drained
+ * so the id upload of step i+1 and the result download of step i-1 both overlap the kernels of step i.
+ * All handles are the caller's CUDA objects (cudaGraphExec_t, cudaStream_t, cudaEvent_t as void*); events must
+ * have been recorded at least once; host buffers should be pinned.
  * --------------------------------------------------------------------------------------------- */
 int32_t gs_pipeline_step(const void* ids_host, void* ids_dev, int64_t ids_bytes, void* const* graph_execs_host,
                          int32_t n_graphs, const void* out_dev, void* out_host, int64_t out_bytes,
-                         void* compute_stream, void* copy_stream, void* ev_done, void* ev_drained);
+                         void* h2d_stream, void* compute_stream, void* copy_stream, void* ev_ids, void* ev_done,
+                         void* ev_drained);
 
 /* tf.nn.l2_normalize(x, 1)   reference graphsage/models.py:368-370, supervised_models.py:85 */
 int32_t gs_l2_normalize_rows(float* x, int64_t n, int32_t C, int64_t ldx, void* stream);
