@@ -248,21 +248,36 @@ def main():
                     a.mlp_layers[0].vars["bias"] = torch.from_numpy(v).to(dev)
                 else:
                     a.vars[k_] = torch.from_numpy(v).to(dev)
-        runner = mdl.graphed(BATCH, normalize=True, probe=probe_name)     # CUDA-graph replay of forward()
+        # ---- timed region 1 ("value"): ids resident in HBM, one CUDA graph per step
+        runner = mdl.graphed(BATCH, normalize=True)
         for i in range(args.warmup):
             runner(seeds_dev[i])
         barrier()
         clocks = ClockSampler(local_rank)
         clocks.start()
-        pev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            out = runner(seeds_dev[args.warmup + i])
+        e1.record()
+        barrier()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        clk = clocks.summary()
+        launches_per_step = runner.launches_per_replay
+        runner.close()
+        # ---- timed region 2 (roofline): same steps with the dominant kernel isolated in its own graph node and
+        #      bracketed by CUDA events on the launching stream (the split costs two extra graph launches per step)
+        runner = mdl.graphed(BATCH, normalize=True, probe=probe_name)
+        for i in range(min(args.warmup, 5)):
+            runner(seeds_dev[i])
+        barrier()
+        pev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         e0.record()
         for i in range(args.steps):
             out = runner(seeds_dev[args.warmup + i], probe_events=pev[i])
         e1.record()
         barrier()
-        ms_total = max_over_ranks(e0.elapsed_time(e1))
-        clk = clocks.summary()
+        ms_probe_total = max_over_ranks(e0.elapsed_time(e1))
         runner.close()
         # end to end through the public host-buffer API: pinned ids in, result in pinned host memory, every step
         pipe = mdl.pipelined(BATCH, normalize=True)
@@ -282,7 +297,8 @@ def main():
         chk = float(out_host[-1].abs().sum())                  # the host really received the last result
         assert np.isfinite(chk) and chk > 0
         kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in pev]))
-        res = dict(ms_total=ms_total, ms_e2e=ms_e2e, clocks=clk, launches=runner.launches_per_replay * args.steps,
+        res = dict(ms_total=ms_total, ms_e2e=ms_e2e, clocks=clk, launches=launches_per_step * args.steps,
+                   ms_probe_step=ms_probe_total / args.steps,
                    gather_kernel_ms=max_over_ranks(kernel_ms), value=world * BATCH * args.steps / (ms_total * 1e-3),
                    e2e=world * BATCH * args.steps / (ms_e2e * 1e-3))
         return res
@@ -332,14 +348,16 @@ def main():
         roof = {"bound": "tensor", "kernel": "maxpool_mlp_kernel (layer 0, hop 2: gather + MLP + ReLU + max over 25)",
                 "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None,
                 "peak_source": "measured sustained cuBLAS bf16 (MEASURED_PEAKS.json)", "avg_kernel_ms": avg_ms,
-                "algorithmic_flops_per_launch": flops, "kernel_share_of_step": avg_ms / (ms_total / args.steps)}
+                "algorithmic_flops_per_launch": flops, "kernel_share_of_step": avg_ms / rep["ms_probe_step"]}
     elif rep["gather_kernel_ms"] > 0:
         avg_ms = rep["gather_kernel_ms"]
         achieved = GATHER_BYTES / (avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "gather_mean (layer 0, hops 0+1)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "avg_kernel_ms": avg_ms, "algorithmic_bytes_per_launch": GATHER_BYTES,
-                "kernel_share_of_step": avg_ms / (ms_total / args.steps)}
+                "kernel_share_of_step": avg_ms / rep["ms_probe_step"],
+                "measured_in": "second timed pass of the same steps with this kernel isolated in its own CUDA-graph node "
+                               "(%.1f us/step there)" % (rep["ms_probe_step"] * 1e3)}
     kernel_ms = {probe_name: rep["gather_kernel_ms"]}
     cpu = None
     if world == 1 and args.cpu_batches > 0:
