@@ -20,12 +20,17 @@
 
 namespace gs {
 
-constexpr int MP_SA = 3;                      // A stages (16 KB each)
-constexpr int MP_MAX_KB = 10;                 // resident weight K-blocks (K <= 640)
+// K-blocks are 32 bf16 columns = 64-byte operand rows (UMMA K-major SWIZZLE_64B): an 8 KB stage instead of 16 KB, so
+// six A stages fit beside the resident weights (with 16 KB stages only three did, and the stage a producer needed
+// next was always the one whose MMA had just been published - a structural bubble), and K pads to 32, not 64.
+constexpr int MP_KCOLS = 32;                  // bf16 columns per K-block
+constexpr int MP_IMG = TC_BM * 64;            // one operand K-block image: 128 rows x 64 B
+constexpr int MP_MAX_KB = 20;                 // resident weight K-blocks (K <= 640)
+constexpr int MP_RING = 26;                   // 8 KB slots shared by the resident weights (kblocks) and the A stages
 constexpr int MP_PROD_WARPS = 4;               // gather-A producer warps
 constexpr int MP_THREADS = (MP_PROD_WARPS + 6) * 32;
 constexpr int MP_STAGE_LD = 129;              // padded row length of the epilogue staging [32][129]
-constexpr int MP_SMEM = MP_MAX_KB * TC_TILE_BYTES + MP_SA * TC_TILE_BYTES + 32 * MP_STAGE_LD * 4 + 1024;
+constexpr int MP_SMEM = MP_RING * MP_IMG + 32 * MP_STAGE_LD * 4 + 1024;
 
 struct MpParams {
   const __nv_bfloat16* table;   // [n_rows, pitch]
@@ -44,14 +49,29 @@ struct MpParams {
   int64_t ldo;
 };
 
-// Wm [K, hidden] row-major fp32 -> bf16 tile images of Wm^T (128 hidden rows x 64 k, K-major, SW128)
+// byte offset of 16-byte chunk c (0..3) of row r inside a K-major SWIZZLE_64B image (Swizzle<2,4,3>: address bits
+// [4,6) ^= bits [7,9); rows are 64 B apart, so bits [7,9) = (r >> 1) & 3)
+__host__ __device__ __forceinline__ uint32_t sw64_off(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
+
+// K-major SWIZZLE_64B shared-memory matrix descriptor: SBO = 8 rows x 64 B = 512 B, layout type 4
+__device__ __forceinline__ uint64_t make_smem_desc64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+
+// Wm [K, hidden] row-major fp32 -> bf16 tile images of Wm^T (128 hidden rows x 32 k, K-major, SW64)
 __global__ void __launch_bounds__(256) maxpool_pack_kernel(const float* __restrict__ W, int64_t ldw, int K, int hidden,
                                                            int kblocks, unsigned char* __restrict__ img) {
   const int slice = blockIdx.x / kblocks, kb = blockIdx.x % kblocks;
-  unsigned char* dst = img + ((int64_t)slice * kblocks + kb) * TC_TILE_BYTES;
-  for (int q = threadIdx.x; q < 128 * 8; q += blockDim.x) {
+  unsigned char* dst = img + ((int64_t)slice * kblocks + kb) * MP_IMG;
+  for (int q = threadIdx.x; q < 128 * 4; q += blockDim.x) {
     const int c = q >> 7, n = q & 127;
-    const int gn = slice * 128 + n, k0 = kb * 64 + c * 8;
+    const int gn = slice * 128 + n, k0 = kb * MP_KCOLS + c * 8;
     __nv_bfloat162 h[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -59,7 +79,7 @@ __global__ void __launch_bounds__(256) maxpool_pack_kernel(const float* __restri
       float b = (gn < hidden && k0 + 2 * e + 1 < K) ? W[(int64_t)(k0 + 2 * e + 1) * ldw + gn] : 0.f;
       h[e] = __floats2bfloat162_rn(a, b);
     }
-    *reinterpret_cast<uint4*>(dst + sw128_off(n, c)) = *reinterpret_cast<uint4*>(h);
+    *reinterpret_cast<uint4*>(dst + sw64_off(n, c)) = *reinterpret_cast<uint4*>(h);
   }
 }
 
@@ -73,15 +93,19 @@ __device__ __forceinline__ void mp_stamp(uint32_t tcount, int slot) {
   }
 }
 
+// MP_SA A stages of 8 KB, MP_INFLIGHT cp.async K-blocks in flight per producer thread: <7, 5> when the resident
+// weights need <= 19 slots (K <= 608), else <6, 4>
+template <int MP_SA, int MP_INFLIGHT>
 __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid_constant__ MpParams prm) {
+  static_assert(MP_INFLIGHT + 2 <= MP_SA, "a stage must be free while MP_INFLIGHT copies fly and one is consumed");
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_a[MP_SA], empty_a[MP_SA], acc_full[2], acc_empty[2], b_full;
   __shared__ uint32_t tmem_base_smem;
   __shared__ float bias_s[128];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* b_res = smem;                                        // resident weight slice
-  unsigned char* a_ring = smem + MP_MAX_KB * TC_TILE_BYTES;
-  float* stage = reinterpret_cast<float*>(a_ring + MP_SA * TC_TILE_BYTES);
+  unsigned char* a_ring = smem + (MP_RING - MP_SA) * MP_IMG;
+  float* stage = reinterpret_cast<float*>(smem + MP_RING * MP_IMG);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slice = blockIdx.x % prm.n_slices;
@@ -112,11 +136,10 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
   if (warp < MP_PROD_WARPS) {
     // =============================== gather-A producers ===============================
     const int tid = threadIdx.x;                    // 0..127
-    const int c = tid & 7, r0 = tid >> 3;           // chunk column, first row; rows r0 + 16 i
+    const int c = tid & 3, r0 = tid >> 2;           // 16-byte chunk of the 64-byte row; rows r0 + 32 i, i < 4
     const int rows_valid = prm.G * prm.k;
     uint32_t it = 0;                                // running K-block counter across tiles (stage / phase)
     int pending = 0;                                // K-blocks issued but not yet published
-    // pipeline state for publishing: we publish K-block (it - 2) after issuing K-block it
     auto publish = [&](uint32_t which) {
       const int s = which % MP_SA;
       fence_proxy_async();
@@ -126,10 +149,10 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
     uint32_t ptile = 0;
     for (int64_t t = tile0; t < prm.n_tiles; t += tile_step, ++ptile) {
       if (threadIdx.x == 0) mp_stamp(ptile, 0);
-      const __nv_bfloat16* rowp[8];
+      const __nv_bfloat16* rowp[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = r0 + 16 * i;
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + 32 * i;
         const int64_t flat = t * rows_valid + r;    // index into the (group, j) row list
         rowp[i] = nullptr;
         if (r < rows_valid && flat < prm.n_groups * prm.k) {
@@ -141,28 +164,35 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
       for (int kb = 0; kb < kblocks; ++kb, ++it) {
         const int s = it % MP_SA;
         mbar_wait(&empty_a[s], ((it / MP_SA) & 1u) ^ 1u);
-        unsigned char* a_img = a_ring + (size_t)s * TC_TILE_BYTES;
-        const int col = kb * 64 + c * 8;            // first bf16 column of this 16-byte piece
+        unsigned char* a_img = a_ring + (size_t)s * MP_IMG;
+        const int col = kb * MP_KCOLS + c * 8;      // first bf16 column of this 16-byte piece
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 4; ++i) {
           int nbytes = 0;
           if (rowp[i] != nullptr && col < prm.K) nbytes = min(8, prm.K - col) * 2;
           const void* src = nbytes ? (const void*)(rowp[i] + col) : (const void*)prm.table;
-          cp_async16(a_img + sw128_off(r0 + 16 * i, c), src, nbytes);
+          cp_async16(a_img + sw64_off(r0 + 32 * i, c), src, nbytes);
         }
         cp_async_commit();
         ++pending;
-        if (pending == 3) {                         // two K-blocks stay in flight; the oldest is complete now
-          cp_async_wait<2>();
-          publish(it - 2);
+        if (pending == MP_INFLIGHT + 1) {           // MP_INFLIGHT K-blocks stay in flight; the oldest has landed
+          cp_async_wait<MP_INFLIGHT>();
+          publish(it - MP_INFLIGHT);
           --pending;
         }
       }
       if (threadIdx.x == 0) mp_stamp(ptile, 1);
     }
-    // drain
-    if (pending == 2) { cp_async_wait<1>(); publish(it - 2); --pending; }
-    if (pending == 1) { cp_async_wait<0>(); publish(it - 1); --pending; }
+    // drain: publish the remaining K-blocks oldest first
+    while (pending > 0) {
+      if (pending >= 5) cp_async_wait<4>();
+      else if (pending == 4) cp_async_wait<3>();
+      else if (pending == 3) cp_async_wait<2>();
+      else if (pending == 2) cp_async_wait<1>();
+      else cp_async_wait<0>();
+      publish(it - pending);
+      --pending;
+    }
   } else if (warp == MP_PROD_WARPS) {
     // =============================== MMA issuer ===============================
     constexpr uint32_t idesc = make_idesc(1u, TC_BM, TC_BN);          // bf16 x bf16 -> fp32
@@ -180,11 +210,11 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
         mbar_wait(&full_a[s], (it / MP_SA) & 1u);
         tc_fence_after();
         if (lane == 0) {
-          const uint64_t adesc = make_smem_desc(smem_u32(a_ring + (size_t)s * TC_TILE_BYTES));
-          const uint64_t bdesc = make_smem_desc(smem_u32(b_res + (size_t)kb * TC_TILE_BYTES));
+          const uint64_t adesc = make_smem_desc64(smem_u32(a_ring + (size_t)s * MP_IMG));
+          const uint64_t bdesc = make_smem_desc64(smem_u32(b_res + (size_t)kb * MP_IMG));
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)
-            umma_ss<true>(tmem_acc, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), idesc, (kb > 0 || k4 > 0) ? 1u : 0u);
+          for (int k2 = 0; k2 < 2; ++k2)            // two K = 16 steps per 32-column K-block (32 B apart inside the atom)
+            umma_ss<true>(tmem_acc, adesc + (uint64_t)(k2 * 2), bdesc + (uint64_t)(k2 * 2), idesc, (kb > 0 || k2 > 0) ? 1u : 0u);
           umma_commit(&empty_a[s]);
           if (kb == kblocks - 1) umma_commit(&acc_full[buf]);
           if (kb == kblocks - 1) mp_stamp(tcount, 4);
@@ -195,10 +225,10 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
   } else if (warp == MP_PROD_WARPS + 1) {
     // =============================== resident weight slice ===============================
     if (lane == 0) {
-      mbar_expect_tx(&b_full, (uint32_t)(kblocks * TC_TILE_BYTES));
-      const unsigned char* src = prm.wimg + (int64_t)slice * kblocks * TC_TILE_BYTES;
+      mbar_expect_tx(&b_full, (uint32_t)(kblocks * MP_IMG));
+      const unsigned char* src = prm.wimg + (int64_t)slice * kblocks * MP_IMG;
       for (int kb = 0; kb < kblocks; ++kb)
-        bulk_g2s(b_res + (size_t)kb * TC_TILE_BYTES, src + (int64_t)kb * TC_TILE_BYTES, TC_TILE_BYTES, &b_full);
+        bulk_g2s(b_res + (size_t)kb * MP_IMG, src + (int64_t)kb * MP_IMG, MP_IMG, &b_full);
     }
     __syncwarp();
   } else {
@@ -278,14 +308,14 @@ int32_t gs_debug_read_maxpool_timeline(unsigned long long* out_host, int32_t n) 
 
 int64_t gs_maxpool_mlp_workspace_bytes(int32_t K, int32_t hidden) {
   if (K < 1 || hidden < 1) return -1;
-  const int kblocks = (K + 63) / 64, slices = (hidden + 127) / 128;
-  return (int64_t)kblocks * slices * gs::TC_TILE_BYTES;
+  const int kblocks = (K + gs::MP_KCOLS - 1) / gs::MP_KCOLS, slices = (hidden + 127) / 128;
+  return (int64_t)kblocks * slices * gs::MP_IMG;
 }
 
 int32_t gs_maxpool_mlp_pack(const float* Wm, int64_t ldw, int32_t K, int32_t hidden, void* workspace, void* stream) {
   GS_REQUIRE(Wm && workspace && K >= 1 && hidden >= 1 && ldw >= hidden, "gs_maxpool_mlp_pack: bad arguments");
   GS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 127u) == 0, "gs_maxpool_mlp_pack: workspace must be 128-byte aligned");
-  const int kblocks = (K + 63) / 64, slices = (hidden + 127) / 128;
+  const int kblocks = (K + gs::MP_KCOLS - 1) / gs::MP_KCOLS, slices = (hidden + 127) / 128;
   gs::maxpool_pack_kernel<<<kblocks * slices, 256, 0, (cudaStream_t)stream>>>(Wm, ldw, K, hidden, kblocks,
                                                                              (unsigned char*)workspace);
   return gs::launch_check("maxpool_pack_kernel");
@@ -301,16 +331,16 @@ int32_t gs_maxpool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K, 
   GS_REQUIRE((pitch * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(table_bf16) & 15u) == 0,
              "gs_maxpool_mlp_fused: table rows must be 16-byte multiples and 16-byte aligned (pitch %% 8 == 0)");
   GS_REQUIRE((reinterpret_cast<uintptr_t>(packed_weights) & 127u) == 0, "gs_maxpool_mlp_fused: packed weights misaligned");
-  if (k > 128 || (K + 63) / 64 > gs::MP_MAX_KB || hidden % 128 != 0) {
+  if (k > 128 || (K + gs::MP_KCOLS - 1) / gs::MP_KCOLS > gs::MP_MAX_KB || hidden % 128 != 0) {
     gs::set_error("gs_maxpool_mlp_fused: needs k <= 128, K <= %d, hidden %% 128 == 0 (k=%d K=%d hidden=%d)",
-                  gs::MP_MAX_KB * 64, k, K, hidden);
+                  gs::MP_MAX_KB * gs::MP_KCOLS, k, K, hidden);
     return GS_ERR_UNSUPPORTED;
   }
   GS_REQUIRE(ldo >= hidden, "gs_maxpool_mlp_fused: ldo < hidden");
   gs::MpParams prm;
   memset(&prm, 0, sizeof(prm));
   prm.table = (const __nv_bfloat16*)table_bf16;
-  prm.n_rows = n_rows; prm.pitch = pitch; prm.K = K; prm.kblocks = (K + 63) / 64;
+  prm.n_rows = n_rows; prm.pitch = pitch; prm.K = K; prm.kblocks = (K + gs::MP_KCOLS - 1) / gs::MP_KCOLS;
   prm.row_ids = row_ids; prm.row0 = row0; prm.n_groups = n_groups; prm.k = k; prm.G = 128 / k;
   prm.n_tiles = (n_groups + prm.G - 1) / prm.G;
   prm.hidden = hidden; prm.n_slices = hidden / 128;
@@ -318,13 +348,17 @@ int32_t gs_maxpool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K, 
   prm.prefetch = gs::tuning("maxpool_prefetch", 1);
   static bool attr_set = false;
   if (!attr_set) {
-    GS_CUDA(cudaFuncSetAttribute(gs::maxpool_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gs::MP_SMEM));
+    GS_CUDA(cudaFuncSetAttribute(gs::maxpool_mlp_kernel<7, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs::MP_SMEM));
+    GS_CUDA(cudaFuncSetAttribute(gs::maxpool_mlp_kernel<6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs::MP_SMEM));
     attr_set = true;
   }
   int64_t ctas = (int64_t)(gs::sm_count() / prm.n_slices) * prm.n_slices;   // a whole number of slice groups
   if (ctas < prm.n_slices) ctas = prm.n_slices;
   if (ctas > prm.n_tiles * prm.n_slices) ctas = prm.n_tiles * prm.n_slices;
-  gs::maxpool_mlp_kernel<<<(unsigned)ctas, gs::MP_THREADS, gs::MP_SMEM, (cudaStream_t)stream>>>(prm);
+  if (prm.kblocks <= gs::MP_RING - 7)
+    gs::maxpool_mlp_kernel<7, 5><<<(unsigned)ctas, gs::MP_THREADS, gs::MP_SMEM, (cudaStream_t)stream>>>(prm);
+  else
+    gs::maxpool_mlp_kernel<6, 4><<<(unsigned)ctas, gs::MP_THREADS, gs::MP_SMEM, (cudaStream_t)stream>>>(prm);
   return gs::launch_check("maxpool_mlp_kernel");
 }
 
