@@ -352,8 +352,21 @@ def main():
     elif rep["gather_kernel_ms"] > 0:
         avg_ms = rep["gather_kernel_ms"]
         achieved = GATHER_BYTES / (avg_ms * 1e-3) / 1e9
+        traffic = None                      # dram__bytes_read + dram__bytes_write of this kernel, committed ncu capture
+        prof = os.path.join(ROOT, "profiles", "ncu_gather_r01_summary.txt")
+        if os.path.exists(prof):
+            vals = {}
+            for line in open(prof):
+                if line.strip() == "" and vals:
+                    break                                    # first kernel record = the layer-0 launch
+                if line.startswith("dram__bytes_") and "=" in line:
+                    k_, v_ = line.split("=")
+                    vals[k_.strip()] = float(v_.split()[0]) * 1e6
+            if len(vals) == 2:
+                traffic = sum(vals.values())
         roof = {"bound": "hbm", "kernel": "gather_mean (layer 0, hops 0+1)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "profiles/ncu_gather_r01_summary.txt (ncu --set full, one launch; bytes)", "peak_source": peak_src,
                 "avg_kernel_ms": avg_ms, "algorithmic_bytes_per_launch": GATHER_BYTES,
                 "kernel_share_of_step": avg_ms / rep["ms_probe_step"],
                 "measured_in": "second timed pass of the same steps with this kernel isolated in its own CUDA-graph node "
