@@ -300,7 +300,10 @@ class PipelinedForward(object):
         self.model, self.depth = model, int(depth)
         self.runners = [GraphedForward(model, batch_size, normalize, first_step=r, step_stride=self.depth)
                         for r in range(self.depth)]
-        self.compute = torch.cuda.Stream(device=dev)
+        # one compute stream per runner: consecutive steps are independent (own ids / outputs / RNG counter), so the
+        # sampler + gather of step i+1 may overlap the GEMM / last layer of step i on SMs the latter leaves idle
+        self.computes = [torch.cuda.Stream(device=dev) for _ in range(self.depth)]
+        self.compute = self.computes[0]
         self.copy = torch.cuda.Stream(device=dev)
         self.h2d = torch.cuda.Stream(device=dev)
         self.ids_ready = [torch.cuda.Event() for _ in range(self.depth)]
@@ -309,7 +312,8 @@ class PipelinedForward(object):
         self.step = 0
         import os
         self.use_c_step = os.environ.get("GS_PIPELINE_PY", "0") != "1"     # GS_PIPELINE_PY=1: torch-API path (debug)
-        self.compute.wait_stream(torch.cuda.current_stream(dev))
+        for c in self.computes:
+            c.wait_stream(torch.cuda.current_stream(dev))
         for e in self.drained + self.done + self.ids_ready:   # also creates the underlying CUDA events
             e.record(self.compute)
 
@@ -338,24 +342,33 @@ class PipelinedForward(object):
             execs, n, ids_dev, ids_bytes, out_dev, out_bytes, ev_ids, ev_done, ev_drained = hs[r]
             ops.check(ops.lib().gs_pipeline_step(ids_host.data_ptr(), ids_dev, ids_bytes, execs, n, out_dev,
                                                  out_host.data_ptr(), out_bytes, self.h2d.cuda_stream,
-                                                 self.compute.cuda_stream, self.copy.cuda_stream, ev_ids, ev_done,
+                                                 self.computes[r].cuda_stream, self.copy.cuda_stream, ev_ids, ev_done,
                                                  ev_drained))
             run.replays += 1
             self.step += 1
             return
-        with torch.cuda.stream(self.compute):
-            self.compute.wait_event(self.drained[r])          # this runner's previous result has left the device
+        with torch.cuda.stream(self.computes[r]):
+            self.computes[r].wait_event(self.drained[r])      # this runner's previous result has left the device
             out = run(ids_host)                               # async H2D of the ids + graph replay
-            self.done[r].record(self.compute)
+            self.done[r].record(self.computes[r])
         with torch.cuda.stream(self.copy):
             self.copy.wait_event(self.done[r])
             out_host.copy_(out, non_blocking=True)
             self.drained[r].record(self.copy)
         self.step += 1
 
+    def submit_device(self, ids_dev):
+        """Device-resident variant: ids already in HBM, result stays in the runner's output buffer (returned)."""
+        r = self.step % self.depth
+        with torch.cuda.stream(self.computes[r]):
+            out = self.runners[r](ids_dev)
+        self.step += 1
+        return out
+
     def synchronize(self):
         self.h2d.synchronize()
-        self.compute.synchronize()
+        for c in self.computes:
+            c.synchronize()
         self.copy.synchronize()
 
     def close(self):
