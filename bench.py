@@ -162,6 +162,8 @@ def main():
     ap.add_argument("--math", default=os.environ.get("GS_MATH", "tf32x3"),
                     help="tf32x3 (tcgen05, fp32-grade: meets the 1e-4 parity bar) | fp32 (CUDA cores) | tf32 | bf16")
     ap.add_argument("--cpu-batches", type=int, default=12)
+    ap.add_argument("--depth", type=int, default=int(os.environ.get("GS_PIPE_DEPTH", "2")),
+                    help="graph runners / compute streams alternating in the pipelined front end")
     ap.add_argument("--no-partitioned", action="store_true", help="skip the node-partitioned measurement at N > 1")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -250,7 +252,7 @@ def main():
                     a.vars[k_] = torch.from_numpy(v).to(dev)
         # ---- timed region 1 ("value"): ids resident in HBM, one CUDA graph per step; two runners alternate on two
         #      streams (steps are independent), so one step's sampler + gather overlaps the previous step's GEMMs
-        pipe = mdl.pipelined(BATCH, normalize=True)
+        pipe = mdl.pipelined(BATCH, normalize=True, depth=args.depth)
         cur = torch.cuda.current_stream(dev)
         for i in range(args.warmup):
             pipe.submit_device(seeds_dev[i])
@@ -290,7 +292,7 @@ def main():
         ms_probe_total = max_over_ranks(e0.elapsed_time(e1))
         runner.close()
         # end to end through the public host-buffer API: pinned ids in, result in pinned host memory, every step
-        pipe = mdl.pipelined(BATCH, normalize=True)
+        pipe = mdl.pipelined(BATCH, normalize=True, depth=args.depth)
         for i in range(min(args.warmup, 6)):
             pipe.submit(seeds_host[i], out_host[i % args.steps])
         pipe.synchronize()
@@ -392,7 +394,7 @@ def main():
         "metric": "seed_nodes_per_sec", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if kind == "maxpool" else "f32", "data": "synthetic",
-        "config": {"workload": workload, "math": args.math, "parallelism": "replicated-table dp%d" % world,
+        "config": {"workload": workload, "math": args.math, "pipeline_depth": args.depth, "parallelism": "replicated-table dp%d" % world,
                    "l2": "inputs larger than L2 (567 MB feature table vs 126 MB L2; fresh random seeds every step)"},
         "e2e": {"value": e2e_value, "unit": "nodes/s", "h2d_bytes_per_step": BATCH * 4,
                 "d2h_bytes_per_step": BATCH * 2 * DIM * 4, "ms_per_step": ms_e2e / args.steps},
