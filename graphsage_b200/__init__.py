@@ -10,5 +10,6 @@ from .layers import Dense, Layer, identity, relu  # noqa: F401
 from .models import SAGEInfo, SampleAndAggregate  # noqa: F401
 from .neigh_samplers import CSRNeighborSampler, UniformNeighborSampler  # noqa: F401
 from .supervised_models import SupervisedGraphsage  # noqa: F401
+from .unsupervised_models import UnigramNegativeSampler, UnsupervisedGraphsage  # noqa: F401
 
 __version__ = "0.1.0"

@@ -161,6 +161,24 @@ __global__ void __launch_bounds__(256) sample_csr_kernel(const int64_t* __restri
   }
 }
 
+// negatives proportional to deg^0.75 (reference models.py:336-343): inverse-CDF lookup, one thread per draw
+__global__ void __launch_bounds__(128) sample_unigram_kernel(const double* __restrict__ cdf, int64_t n, int32_t num,
+                                                             uint64_t seed, uint64_t counter,
+                                                             const uint64_t* __restrict__ counter_dev,
+                                                             int32_t* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= num) return;
+  const uint64_t ctr = counter + (counter_dev ? *counter_dev : 0ull);
+  const uint32_t r = philox_draw(seed, ctr, 0u, kStreamUnigram, j);
+  const double u = ((double)r + 0.5) * (1.0 / 4294967296.0) * cdf[n - 1];
+  int64_t lo = 0, hi = n - 1;                       // first index with cdf[index] > u
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (cdf[mid] > u) hi = mid; else lo = mid + 1;
+  }
+  out[j] = (int32_t)lo;
+}
+
 }  // namespace gs
 
 extern "C" {
@@ -213,6 +231,16 @@ int32_t gs_sample_padded_khop(const int32_t* adj, int64_t n_rows, int32_t max_de
   gs::sample_padded_khop_kernel<<<(unsigned)blocks, 512, 0, (cudaStream_t)stream>>>(adj, n_rows, max_deg, seeds, kp, seed,
                                                                                     counter, counter_dev);
   return gs::launch_check("sample_padded_khop_kernel");
+}
+
+int32_t gs_sample_unigram(const double* cdf, int64_t n, int32_t num_sampled, uint64_t seed, uint64_t counter,
+                          const uint64_t* counter_dev, int32_t* out, void* stream) {
+  GS_REQUIRE(num_sampled >= 0 && n >= 1, "gs_sample_unigram: bad sizes");
+  if (num_sampled == 0) return GS_OK;
+  GS_REQUIRE(cdf && out, "gs_sample_unigram: NULL pointer");
+  gs::sample_unigram_kernel<<<(num_sampled + 127) / 128, 128, 0, (cudaStream_t)stream>>>(cdf, n, num_sampled, seed, counter,
+                                                                                       counter_dev, out);
+  return gs::launch_check("sample_unigram_kernel");
 }
 
 int32_t gs_sample_csr(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, const int32_t* ids, int64_t n,

@@ -85,6 +85,19 @@ def sample_padded_khop(adj, seeds, fanouts, seed, counter, counter_dev=None):
     return outs
 
 
+def sample_unigram(cdf, num_sampled, seed, counter, counter_dev=None):
+    """tf.nn.fixed_unigram_candidate_sampler(unique=False) - reference graphsage/models.py:336-343.
+    cdf: float64 CUDA tensor, inclusive prefix sum of the (distorted) unigram weights."""
+    require_cuda(cdf, counter_dev)
+    if cdf.dtype != torch.float64:
+        raise TypeError("cdf must be float64")
+    out = torch.empty((num_sampled,), dtype=torch.int32, device=cdf.device)
+    check(lib().gs_sample_unigram(ptr(cdf), cdf.numel(), num_sampled, seed & _U64, counter & _U64, ptr(counter_dev),
+                                  ptr(out), stream_ptr()))
+    _launched(1 if num_sampled else 0)
+    return out
+
+
 def sample_csr(indptr, indices, ids, k, seed, counter, replace_if_short=True, pad_id=-1, counter_dev=None):
     require_cuda(indptr, indices, ids)
     if indptr.dtype != torch.int64:

@@ -80,6 +80,50 @@ class _AggregateRowsFn(torch.autograd.Function):
         return (None, dsrc, None) + tuple(grads_w)
 
 
+def differentiable_outputs(model, batch, normalize=True):
+    """sample -> aggregate (-> l2_normalize) with an autograd graph over the aggregator weights; `model` is a
+    SampleAndAggregate whose .aggregators exist (reference models.py:347-350 / supervised_models.py:79-85)."""
+    batch = batch.to(device=model.device, dtype=torch.int32).reshape(-1)
+    n = batch.numel()
+    with torch.no_grad():
+        samples, support = model.sample(batch, model.layer_infos, batch_size=n)
+    num_samples = [info.num_samples for info in model.layer_infos]
+    L = len(num_samples)
+    counts = [n * support[h] for h in range(L + 1)]
+    src = model.features
+    for layer in range(L):
+        hops = L - layer
+        row0 = [sum(counts[:h]) for h in range(hops + 1)]
+        segs = []
+        for hop in range(hops):
+            k = num_samples[L - hop - 1]
+            if layer == 0:
+                segs.append(ops.Seg(counts[hop], k, self_ids=samples[hop], neigh_ids=samples[hop + 1],
+                                    out_row0=row0[hop]))
+            else:
+                segs.append(ops.Seg(counts[hop], k, self_row0=row0[hop], neigh_row0=row0[hop + 1],
+                                    out_row0=row0[hop]))
+        agg = model.aggregators[layer]
+        ws = (agg.vars["weights"],) if "weights" in agg.vars else (agg.vars["self_weights"], agg.vars["neigh_weights"])
+        src = _AggregateRowsFn.apply(agg, src, segs, *ws)
+    out = src[:counts[0]]
+    if normalize:
+        out = out / torch.sqrt(torch.clamp((out * out).sum(dim=1, keepdim=True), min=1e-12))   # tf.nn.l2_normalize
+    return out
+
+
+def build_aggregators(model):
+    """One aggregator per layer, as SampleAndAggregate.aggregate creates them (reference models.py:303-315)."""
+    L = len(model.layer_infos)
+    aggs = []
+    for layer in range(L):
+        dim_mult = 2 if model.concat and layer != 0 else 1
+        act = identity if layer == L - 1 else relu
+        aggs.append(model.aggregator_cls(dim_mult * model.dims[layer], model.dims[layer + 1], act=act, dropout=0.,
+                                         concat=model.concat, device=model.device))
+    return aggs
+
+
 class SupervisedGraphsage(SampleAndAggregate):
     """Supervised GraphSAGE (reference graphsage/supervised_models.py:10-126): the hot path, then
     l2_normalize -> Dense(-> num_classes) -> sigmoid / softmax cross-entropy (+ weight decay), gradients clipped to
@@ -100,13 +144,7 @@ class SupervisedGraphsage(SampleAndAggregate):
 
     def build(self):
         from .inits import glorot, zeros
-        L = len(self.layer_infos)
-        self.aggregators = []
-        for layer in range(L):                                                   # models.py:303-315
-            dim_mult = 2 if self.concat and layer != 0 else 1
-            act = identity if layer == L - 1 else relu
-            self.aggregators.append(self.aggregator_cls(dim_mult * self.dims[layer], self.dims[layer + 1], act=act,
-                                                        dropout=0., concat=self.concat, device=self.device))
+        self.aggregators = build_aggregators(self)
         dim_mult = 2 if self.concat else 1
         self.node_pred_vars = {"weights": glorot([dim_mult * self.dims[-1], self.num_classes], device=self.device),
                                "bias": zeros([self.num_classes], device=self.device)}   # supervised_models.py:88-90
@@ -123,31 +161,7 @@ class SupervisedGraphsage(SampleAndAggregate):
 
     def outputs(self, batch):
         """l2-normalised node representations, differentiable (supervised_models.py:79-85)."""
-        batch = batch.to(device=self.device, dtype=torch.int32).reshape(-1)
-        n = batch.numel()
-        with torch.no_grad():
-            samples, support = self.sample(batch, self.layer_infos, batch_size=n)
-        num_samples = [info.num_samples for info in self.layer_infos]
-        L = len(num_samples)
-        counts = [n * support[h] for h in range(L + 1)]
-        src = self.features
-        for layer in range(L):
-            hops = L - layer
-            row0 = [sum(counts[:h]) for h in range(hops + 1)]
-            segs = []
-            for hop in range(hops):
-                k = num_samples[L - hop - 1]
-                if layer == 0:
-                    segs.append(ops.Seg(counts[hop], k, self_ids=samples[hop], neigh_ids=samples[hop + 1],
-                                        out_row0=row0[hop]))
-                else:
-                    segs.append(ops.Seg(counts[hop], k, self_row0=row0[hop], neigh_row0=row0[hop + 1],
-                                        out_row0=row0[hop]))
-            agg = self.aggregators[layer]
-            ws = (agg.vars["weights"],) if "weights" in agg.vars else (agg.vars["self_weights"], agg.vars["neigh_weights"])
-            src = _AggregateRowsFn.apply(agg, src, segs, *ws)
-        out = src[:counts[0]]
-        return out / torch.sqrt(torch.clamp((out * out).sum(dim=1, keepdim=True), min=1e-12))   # tf.nn.l2_normalize
+        return differentiable_outputs(self, batch)
 
     def logits(self, batch):
         return self.outputs(batch) @ self.node_pred_vars["weights"] + self.node_pred_vars["bias"]

@@ -85,6 +85,14 @@ int32_t gs_sample_csr(const int64_t* indptr, const int32_t* indices, int64_t n_n
                       uint64_t seed, uint64_t counter, const uint64_t* counter_dev,
                       int32_t pad_id, int32_t* out, void* stream);
 
+/* tf.nn.fixed_unigram_candidate_sampler(unique=False)   reference graphsage/models.py:336-343
+ *   num_sampled ids drawn with replacement with probability proportional to the weights behind `cdf`
+ *   (cdf[i] = sum_{j<=i} deg[j]^0.75, float64, non-decreasing, length n).  Draw j uses word j&3 of
+ *   Philox4x32-10 block (counter, c2 = 0, GS unigram stream tag + j>>2): u = (draw + 0.5) / 2^32 * cdf[n-1],
+ *   out[j] = first index with cdf[index] > u (oracle/sampler.py:sample_unigram; TF's own stream is unobtainable). */
+int32_t gs_sample_unigram(const double* cdf, int64_t n, int32_t num_sampled, uint64_t seed, uint64_t counter,
+                          const uint64_t* counter_dev, int32_t* out, void* stream);
+
 /* host helper: the first k entries of pi for (seed, counter) - what the kernel computes */
 int32_t gs_perm_prefix_host(uint64_t seed, uint64_t counter, int32_t max_deg, int32_t k,
                             int32_t* out_host);

@@ -21,7 +21,7 @@ Parity status (see DESIGN.md "Oracle"):
     oracle/philox.py) and Eigen's fp32 summation order (tolerance 1e-4 rel).
 """
 from .philox import philox4x32_10, mulhi32
-from .sampler import (perm_prefix, sample_padded, sample_csr,
+from .sampler import (perm_prefix, sample_padded, sample_csr, sample_unigram,
                       STREAM_PADDED, STREAM_CSR)
 from .aggregate import (gather_rows, mean_aggregator, gcn_aggregator,
                         maxpool_aggregator, dense, l2_normalize, glorot_range,

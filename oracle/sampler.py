@@ -32,6 +32,7 @@ from .philox import philox4x32_10, mulhi32, split64
 
 STREAM_PADDED = 0
 STREAM_CSR = 0x40000000
+STREAM_UNIGRAM = 0x20000000
 
 
 def _draws(seed, counter, n_draws, c2=0, tag=STREAM_PADDED):
@@ -102,3 +103,14 @@ def sample_csr(indptr, indices, ids, k, seed, counter, replace_if_short=True, pa
             S[:, j] = np.where(dup, m, t)
         out[rows] = indices[start[rows, None] + S]
     return out
+
+
+def sample_unigram(degrees, num_sampled, seed, counter, distortion=0.75):
+    """tf.nn.fixed_unigram_candidate_sampler(unique=False, distortion=0.75, unigrams=degrees)
+    (reference graphsage/models.py:336-343): num_sampled ids with replacement, P(i) ~ deg[i]^distortion.
+    Contract (TF's stream is unobtainable): draw j = word j&3 of Philox block (counter, c2=0, UNIGRAM tag + j>>2);
+    u = (draw + 0.5) / 2^32 * total;  id = first index whose inclusive float64 prefix sum exceeds u."""
+    cdf = np.cumsum(np.asarray(degrees, dtype=np.float64) ** distortion)
+    r = _draws(seed, counter, num_sampled, c2=0, tag=STREAM_UNIGRAM).astype(np.float64)
+    u = (r + 0.5) * (1.0 / 4294967296.0) * cdf[-1]
+    return np.searchsorted(cdf, u, side="right").astype(np.int32)

@@ -98,3 +98,66 @@ def test_training_steps_track_cpu_adam():
     for a, ra in zip(m.aggregators, aggs):
         for k in a.vars:
             assert rel_err(a.vars[k].detach().cpu().numpy(), ra[k].detach().numpy()) < 5e-3
+
+
+def test_unigram_sampler_bit_exact_and_distribution():
+    import graphsage_b200 as gs
+    import oracle
+    rs = np.random.RandomState(2)
+    deg = rs.randint(0, 300, size=5000).astype(np.float64)
+    deg[:5] = 0
+    s = gs.UnigramNegativeSampler(deg, seed=9)
+    a = s(20).cpu().numpy()
+    b = s(1000).cpu().numpy()
+    np.testing.assert_array_equal(a, oracle.sample_unigram(deg, 20, 9, 0))
+    np.testing.assert_array_equal(b, oracle.sample_unigram(deg, 1000, 9, 1))
+    assert (deg[b] > 0).all()                                    # zero-degree nodes are never drawn
+    big = gs.ops.sample_unigram(s.cdf, 400000, 1, 1).cpu().numpy()
+    p = np.bincount(big, minlength=5000) / 400000.0
+    q = deg ** 0.75 / (deg ** 0.75).sum()
+    assert np.abs(p - q).max() < 5e-4
+
+
+def test_unsupervised_loss_gradients_and_mrr_match_cpu():
+    import graphsage_b200 as gs
+    import oracle
+    g = load_golden("khop")
+    rs = np.random.RandomState(11)
+    adj, feats = g["adj"], g["feats"]
+    n, B, NEG = adj.shape[0] - 1, 16, 20
+    deg = rs.randint(1, 40, size=n).astype(np.float64)
+    b1 = rs.randint(0, n, size=B).astype(np.int32)
+    b2 = rs.randint(0, n, size=B).astype(np.int32)
+    fan, dim = [5, 3], 12
+    gs.set_default_math("fp32")
+    sampler = gs.UniformNeighborSampler(torch.from_numpy(adj).cuda(), seed=123)
+    infos = [gs.SAGEInfo("node", sampler, fan[0], dim), gs.SAGEInfo("node", sampler, fan[1], dim)]
+    m = gs.UnsupervisedGraphsage({"batch_size": B, "dropout": 0.}, torch.from_numpy(feats).cuda(),
+                                 torch.from_numpy(adj).cuda(), deg, infos, concat=True, aggregator_type="mean",
+                                 neg_sample_size=NEG, learning_rate=0.01, weight_decay=1e-3, seed=77)
+    aggs = [{k: v.detach().cpu().clone().requires_grad_(True) for k, v in a.vars.items()} for a in m.aggregators]
+    # CPU restatement: the three passes use sampler counters 0..1, 2..3, 4..5 (two calls each), negatives from counter 0
+    neg = oracle.sample_unigram(deg, NEG, 77, 0)
+    A, F = torch.from_numpy(adj), torch.from_numpy(feats)
+    o1 = torch_ref.forward(A, F, torch.from_numpy(b1), fan, aggs, True, "mean", 123, 0)
+    o2 = torch_ref.forward(A, F, torch.from_numpy(b2), fan, aggs, True, "mean", 123, 2)
+    on = torch_ref.forward(A, F, torch.from_numpy(neg), fan, aggs, True, "mean", 123, 4)
+    aff = (o1 * o2).sum(1)
+    neg_aff = o1 @ on.t()
+    ref = torch.nn.functional.softplus(-aff).sum() + torch.nn.functional.softplus(neg_aff).sum()
+    for a in aggs:
+        for v in a.values():
+            ref = ref + 1e-3 * 0.5 * (v * v).sum()
+    ref = ref / B
+    ref.backward()
+    loss = m.loss(torch.from_numpy(b1), torch.from_numpy(b2))
+    loss.backward()
+    assert abs(float(loss.detach()) - float(ref.detach())) < 1e-5 * max(1.0, abs(float(ref.detach())))
+    for a, ra in zip(m.aggregators, aggs):
+        for k in a.vars:
+            assert rel_err(a.vars[k].grad.cpu().numpy(), ra[k].grad.numpy(), floor=1e-8) < 3e-4, k
+    aff_all = torch.cat([neg_aff.detach(), aff.detach().unsqueeze(1)], dim=1)
+    ranks = torch.argsort(torch.argsort(aff_all, dim=1, descending=True, stable=True), dim=1, stable=True)
+    assert abs(float(m.mrr()) - float((1.0 / (ranks[:, -1] + 1).float()).mean())) < 1e-6
+    l0 = float(m.train_step(torch.from_numpy(b1), torch.from_numpy(b2)))
+    assert np.isfinite(l0)
