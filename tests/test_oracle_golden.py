@@ -143,3 +143,16 @@ def test_torch_cpu_baseline_matches_numpy_oracle():
         out = torch_ref.forward(torch.from_numpy(g["adj"]), torch.from_numpy(g["feats"]), torch.from_numpy(g["seeds"]),
                                 fan, aggs, bool(g[model + "_concat"]), kind, 123, 40, normalize=True)
         assert rel_err(out.numpy(), g[model + "_out_l2"]) < 1e-5
+
+
+def test_unigram_sampler_oracle_distribution():
+    rs = np.random.RandomState(0)
+    deg = rs.randint(0, 100, size=1000).astype(np.float64)
+    x = oracle.sample_unigram(deg, 20, 123, 5)
+    assert x.dtype == np.int32 and (deg[x] > 0).all()
+    np.testing.assert_array_equal(x, oracle.sample_unigram(deg, 20, 123, 5))
+    assert (x != oracle.sample_unigram(deg, 20, 123, 6)).any()
+    big = oracle.sample_unigram(deg, 200000, 1, 1)
+    p = np.bincount(big, minlength=1000) / 200000.0
+    q = deg ** 0.75 / (deg ** 0.75).sum()
+    assert np.abs(p - q).max() < 1e-3
