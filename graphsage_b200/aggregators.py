@@ -231,9 +231,9 @@ class MaxPoolingAggregator(_SageAggregator):
             hmax = torch.empty((rows, self.hidden_dim), dtype=torch.float32, device=dev)
             for s in segments:
                 n = s.n
-                h = ops.maxpool_mlp_fused(table, n, s.k, mlp.vars["weights"], mlp.vars["bias"], self._packed_mlp,
-                                          row_ids=s.neigh_ids, row0=s.neigh_row0, K=self.neigh_input_dim)
-                hmax[s.out_row0:s.out_row0 + n] = h
+                ops.maxpool_mlp_fused(table, n, s.k, mlp.vars["weights"], mlp.vars["bias"], self._packed_mlp,
+                                      row_ids=s.neigh_ids, row0=s.neigh_row0, K=self.neigh_input_dim,
+                                      out=hmax[s.out_row0:s.out_row0 + n])
                 if s.self_ids is not None:
                     xs[s.out_row0:s.out_row0 + n] = ops.gather_rows(src, s.self_ids[:n]).float()
                 else:

@@ -44,7 +44,6 @@ struct MpParams {
   int32_t hidden, n_slices;
   const unsigned char* wimg;    // packed Wm^T: [n_slices][kblocks][16 KB]
   const float* bias;            // [hidden] or NULL
-  int32_t prefetch;             // L2-prefetch the next tile's rows
   float* out;                   // [n_groups, hidden]
   int64_t ldo;
 };
@@ -345,7 +344,6 @@ int32_t gs_maxpool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K, 
   prm.n_tiles = (n_groups + prm.G - 1) / prm.G;
   prm.hidden = hidden; prm.n_slices = hidden / 128;
   prm.wimg = (const unsigned char*)packed_weights; prm.bias = bias; prm.out = out; prm.ldo = ldo;
-  prm.prefetch = gs::tuning("maxpool_prefetch", 1);
   static bool attr_set = false;
   if (!attr_set) {
     GS_CUDA(cudaFuncSetAttribute(gs::maxpool_mlp_kernel<7, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs::MP_SMEM));

@@ -329,7 +329,7 @@ class PackedMlpWeights(object):
         return self.ws
 
 
-def maxpool_mlp_fused(table, n_groups, k, W, bias, packed, row_ids=None, row0=0, K=None):
+def maxpool_mlp_fused(table, n_groups, k, W, bias, packed, row_ids=None, row0=0, K=None, out=None):
     """out[g, :] = max_j relu(table[row(g, j), :K] @ W + bias) in one tcgen05 kernel (bf16 operands, fp32 accumulate).
     table: bfloat16 [rows, >=K] row-major with pitch % 8 == 0; W: float32 [K, hidden] (hidden % 128 == 0)."""
     require_cuda(table, W, bias, row_ids)
@@ -337,7 +337,8 @@ def maxpool_mlp_fused(table, n_groups, k, W, bias, packed, row_ids=None, row0=0,
         raise TypeError("table must be row-major bfloat16")
     K = W.shape[0] if K is None else K
     hidden = W.shape[1]
-    out = torch.empty((n_groups, hidden), dtype=torch.float32, device=table.device)
+    if out is None:
+        out = torch.empty((n_groups, hidden), dtype=torch.float32, device=table.device)
     ws = packed.get(W)
     if row_ids is not None:
         row_ids = _i32(row_ids.reshape(-1), "row_ids")
