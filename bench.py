@@ -154,8 +154,8 @@ def cpu_reference_rate(g, kind, weights, n_batches, warm, seed_rs, budget_s=None
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--aggregator", default="mean", choices=["mean", "gcn", "maxpool"],
                     help="mean = BASELINE configs[1] (default); maxpool (+ bf16 features, --math bf16) = configs[2]")
