@@ -187,11 +187,15 @@ class MaxPoolingAggregator(_SageAggregator):
     def _combine(self):
         return ops.COMBINE_CONCAT if self.concat else ops.COMBINE_ADD
 
+    pool = "max"
+
     def _pool(self, rows, n, k):
         h = rows
         for layer in self.mlp_layers:
             layer.math = self.math
             h = layer(h)
+        if self.pool == "mean":
+            return ops.gather_mean(h, [ops.Seg(n, k)], want_self=False, out_pitch=h.shape[1])[1]
         return ops.segment_max(h, n, k)
 
     def _call(self, inputs):
@@ -233,7 +237,7 @@ class MaxPoolingAggregator(_SageAggregator):
                 n = s.n
                 ops.maxpool_mlp_fused(table, n, s.k, mlp.vars["weights"], mlp.vars["bias"], self._packed_mlp,
                                       row_ids=s.neigh_ids, row0=s.neigh_row0, K=self.neigh_input_dim,
-                                      out=hmax[s.out_row0:s.out_row0 + n])
+                                      out=hmax[s.out_row0:s.out_row0 + n], pool=self.pool)
                 if s.self_ids is not None:
                     xs[s.out_row0:s.out_row0 + n] = ops.gather_rows(src, s.self_ids[:n]).float()
                 else:
@@ -255,3 +259,9 @@ class MaxPoolingAggregator(_SageAggregator):
                 xs[s.out_row0:s.out_row0 + n] = src[s.self_row0:s.self_row0 + n]
         return self._finish([(xs, self.input_dim, self.vars["self_weights"]),
                              (hmax, self.hidden_dim, self.vars["neigh_weights"])], self._combine())
+
+
+class MeanPoolingAggregator(MaxPoolingAggregator):
+    """act(concat_or_add(self @ Ws, mean_k(relu(neigh @ Wm + bm)) @ Wn)) - reference graphsage/aggregators.py:197-273.
+    Same kernels as the max-pool aggregator with the pooling operator swapped."""
+    pool = "mean"

@@ -44,6 +44,7 @@ struct MpParams {
   int32_t hidden, n_slices;
   const unsigned char* wimg;    // packed Wm^T: [n_slices][kblocks][16 KB]
   const float* bias;            // [hidden] or NULL
+  int32_t pool_mean;            // 0: max over the fanout (MaxPoolingAggregator), 1: mean (MeanPoolingAggregator)
   float* out;                   // [n_groups, hidden]
   int64_t ldo;
 };
@@ -265,16 +266,27 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
             const int64_t gg = t * G + g;
             if (gg < prm.n_groups) {
               const float* p = stage + cc * MP_STAGE_LD + g * k;
-              float m = -3.0e38f;
-              int j = 0;
-              for (; j + 8 <= k; j += 8) {
-                float v[8];
+              const float b = bias_s[cb * 32 + cc];
+              float res;
+              if (prm.pool_mean) {
+                // mean-pool (reference aggregators.py:246-273): ReLU does not commute with the mean, so bias + ReLU
+                // are applied per element, summed in j order, divided by k
+                float sacc = 0.f;
+                for (int j = 0; j < k; ++j) sacc += fmaxf(p[j] + b, 0.f);
+                res = sacc / (float)k;
+              } else {
+                float m = -3.0e38f;
+                int j = 0;
+                for (; j + 8 <= k; j += 8) {
+                  float v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = p[j + u];
-                m = fmaxf(m, fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7]))));
+                  for (int u = 0; u < 8; ++u) v[u] = p[j + u];
+                  m = fmaxf(m, fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7]))));
+                }
+                for (; j < k; ++j) m = fmaxf(m, p[j]);
+                res = fmaxf(m + b, 0.f);                                          // Dense bias + ReLU (commute with the max)
               }
-              for (; j < k; ++j) m = fmaxf(m, p[j]);
-              prm.out[gg * prm.ldo + hcol0 + cc] = fmaxf(m + bias_s[cb * 32 + cc], 0.f);   // Dense bias + ReLU
+              prm.out[gg * prm.ldo + hcol0 + cc] = res;
             }
           }
         }
@@ -320,9 +332,9 @@ int32_t gs_maxpool_mlp_pack(const float* Wm, int64_t ldw, int32_t K, int32_t hid
   return gs::launch_check("maxpool_pack_kernel");
 }
 
-int32_t gs_maxpool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K, int64_t pitch, const int32_t* row_ids,
-                             int64_t row0, int64_t n_groups, int32_t k, const void* packed_weights, const float* bias,
-                             int32_t hidden, float* out, int64_t ldo, void* stream) {
+static int32_t pool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K, int64_t pitch, const int32_t* row_ids,
+                              int64_t row0, int64_t n_groups, int32_t k, const void* packed_weights, const float* bias,
+                              int32_t hidden, float* out, int64_t ldo, int32_t pool_mean, void* stream) {
   GS_REQUIRE(n_groups >= 0 && k >= 1, "gs_maxpool_mlp_fused: bad n_groups / k");
   if (n_groups == 0) return GS_OK;
   GS_REQUIRE(table_bf16 && packed_weights && out, "gs_maxpool_mlp_fused: NULL pointer");
@@ -344,6 +356,7 @@ int32_t gs_maxpool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K, 
   prm.n_tiles = (n_groups + prm.G - 1) / prm.G;
   prm.hidden = hidden; prm.n_slices = hidden / 128;
   prm.wimg = (const unsigned char*)packed_weights; prm.bias = bias; prm.out = out; prm.ldo = ldo;
+  prm.pool_mean = pool_mean;
   static bool attr_set = false;
   if (!attr_set) {
     GS_CUDA(cudaFuncSetAttribute(gs::maxpool_mlp_kernel<7, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs::MP_SMEM));
@@ -358,6 +371,20 @@ int32_t gs_maxpool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K, 
   else
     gs::maxpool_mlp_kernel<6, 4><<<(unsigned)ctas, gs::MP_THREADS, gs::MP_SMEM, (cudaStream_t)stream>>>(prm);
   return gs::launch_check("maxpool_mlp_kernel");
+}
+
+int32_t gs_maxpool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K, int64_t pitch, const int32_t* row_ids,
+                             int64_t row0, int64_t n_groups, int32_t k, const void* packed_weights, const float* bias,
+                             int32_t hidden, float* out, int64_t ldo, void* stream) {
+  return pool_mlp_fused(table_bf16, n_rows, K, pitch, row_ids, row0, n_groups, k, packed_weights, bias, hidden, out, ldo, 0,
+                        stream);
+}
+
+int32_t gs_meanpool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K, int64_t pitch, const int32_t* row_ids,
+                              int64_t row0, int64_t n_groups, int32_t k, const void* packed_weights, const float* bias,
+                              int32_t hidden, float* out, int64_t ldo, void* stream) {
+  return pool_mlp_fused(table_bf16, n_rows, K, pitch, row_ids, row0, n_groups, k, packed_weights, bias, hidden, out, ldo, 1,
+                        stream);
 }
 
 }  // extern "C"

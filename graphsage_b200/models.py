@@ -9,7 +9,7 @@ from collections import namedtuple
 import torch
 
 from . import ops
-from .aggregators import GCNAggregator, MaxPoolingAggregator, MeanAggregator
+from .aggregators import GCNAggregator, MaxPoolingAggregator, MeanAggregator, MeanPoolingAggregator
 from .layers import identity, relu  # noqa: F401
 
 # reference graphsage/models.py:180-185
@@ -19,7 +19,8 @@ SAGEInfo = namedtuple("SAGEInfo",
                        "num_samples",
                        "output_dim"])     # the output (i.e., hidden) dimension
 
-_AGGREGATORS = {"mean": MeanAggregator, "maxpool": MaxPoolingAggregator, "gcn": GCNAggregator}
+_AGGREGATORS = {"mean": MeanAggregator, "maxpool": MaxPoolingAggregator, "gcn": GCNAggregator,
+                "meanpool": MeanPoolingAggregator}
 
 
 class SampleAndAggregate(object):
@@ -36,7 +37,7 @@ class SampleAndAggregate(object):
         for kwarg in kwargs.keys():
             assert kwarg in allowed_kwargs, "Invalid keyword argument: " + kwarg   # reference models.py:22-24
         if aggregator_type not in _AGGREGATORS:
-            if aggregator_type in ("seq", "meanpool"):
+            if aggregator_type in ("seq",):
                 raise NotImplementedError("aggregator_type %r is outside the hot path (SURVEY section 2, row 5)"
                                           % aggregator_type)
             raise ValueError("Unknown aggregator: %r" % (aggregator_type,))
@@ -126,7 +127,7 @@ class SampleAndAggregate(object):
                 act = identity if layer == L - 1 else relu                      # models.py:307-310
                 kw = dict(act=act, dropout=self.placeholders.get("dropout", 0.), name=name, concat=concat,
                           device=self.device)
-                if self.aggregator_cls is MaxPoolingAggregator:
+                if issubclass(self.aggregator_cls, MaxPoolingAggregator):
                     kw["model_size"] = model_size
                 aggregators.append(self.aggregator_cls(dim_mult * dims[layer], dims[layer + 1], **kw))
         if any(getattr(a, "dropout", 0.) for a in aggregators):
@@ -172,6 +173,21 @@ class SampleAndAggregate(object):
     def pipelined(self, batch_size, normalize=True, depth=2):
         """Host-buffer, copy/compute-overlapped front end (see PipelinedForward)."""
         return PipelinedForward(self, batch_size, normalize, depth)
+
+    def export_embeddings(self, node_ids, batch_size=512, out_prefix=None):
+        """Embedding export (reference graphsage/unsupervised_train.py:94-117): forward every given node in batches,
+        return float32 [n, out_w]; with out_prefix also write `<prefix>.npy` and `<prefix>.txt` (one id per line)."""
+        import numpy as np
+        ids = torch.as_tensor(node_ids, dtype=torch.int32).reshape(-1)
+        outs = []
+        for i in range(0, ids.numel(), batch_size):
+            outs.append(self.forward(ids[i:i + batch_size], normalize=True).cpu())
+        emb = torch.cat(outs).numpy() if outs else np.zeros((0, 0), np.float32)
+        if out_prefix is not None:
+            np.save(out_prefix + ".npy", emb)
+            with open(out_prefix + ".txt", "w") as fp:
+                fp.write("\n".join(str(int(x)) for x in ids.tolist()))
+        return emb
 
     def forward(self, batch, normalize=True):
         """sample -> aggregate -> l2_normalize (reference models.py:347-350, 368) for one id batch."""

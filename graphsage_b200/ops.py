@@ -329,7 +329,7 @@ class PackedMlpWeights(object):
         return self.ws
 
 
-def maxpool_mlp_fused(table, n_groups, k, W, bias, packed, row_ids=None, row0=0, K=None, out=None):
+def maxpool_mlp_fused(table, n_groups, k, W, bias, packed, row_ids=None, row0=0, K=None, out=None, pool="max"):
     """out[g, :] = max_j relu(table[row(g, j), :K] @ W + bias) in one tcgen05 kernel (bf16 operands, fp32 accumulate).
     table: bfloat16 [rows, >=K] row-major with pitch % 8 == 0; W: float32 [K, hidden] (hidden % 128 == 0)."""
     require_cuda(table, W, bias, row_ids)
@@ -343,8 +343,9 @@ def maxpool_mlp_fused(table, n_groups, k, W, bias, packed, row_ids=None, row0=0,
     if row_ids is not None:
         row_ids = _i32(row_ids.reshape(-1), "row_ids")
     ev = _probe("maxpool_mlp/%d" % n_groups)
-    check(lib().gs_maxpool_mlp_fused(ptr(table), table.shape[0], K, table.stride(0), ptr(row_ids), row0, n_groups, k,
-                                     ptr(ws), ptr(bias), hidden, ptr(out), out.stride(0), stream_ptr()))
+    fn = lib().gs_meanpool_mlp_fused if pool == "mean" else lib().gs_maxpool_mlp_fused
+    check(fn(ptr(table), table.shape[0], K, table.stride(0), ptr(row_ids), row0, n_groups, k,
+             ptr(ws), ptr(bias), hidden, ptr(out), out.stride(0), stream_ptr()))
     _launched(1 if n_groups else 0, ev)
     return out
 

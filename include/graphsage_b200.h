@@ -238,6 +238,12 @@ int32_t gs_maxpool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K, 
                              const int32_t* row_ids, int64_t row0, int64_t n_groups, int32_t k,
                              const void* packed_weights, const float* bias, int32_t hidden,
                              float* out, int64_t ldo, void* stream);
+/* MeanPoolingAggregator's neighbour branch (reference graphsage/aggregators.py:246-273): same kernel, the
+ * epilogue averages relu(x + b) over the fanout instead of taking the max. */
+int32_t gs_meanpool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K, int64_t pitch,
+                              const int32_t* row_ids, int64_t row0, int64_t n_groups, int32_t k,
+                              const void* packed_weights, const float* bias, int32_t hidden,
+                              float* out, int64_t ldo, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * One pipelined step from HOST buffers in a single call (no per-kernel host work), on three streams:

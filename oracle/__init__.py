@@ -24,7 +24,7 @@ from .philox import philox4x32_10, mulhi32
 from .sampler import (perm_prefix, sample_padded, sample_csr, sample_unigram,
                       STREAM_PADDED, STREAM_CSR)
 from .aggregate import (gather_rows, mean_aggregator, gcn_aggregator,
-                        maxpool_aggregator, dense, l2_normalize, glorot_range,
+                        maxpool_aggregator, meanpool_aggregator, dense, l2_normalize, glorot_range,
                         sample_khop, aggregate_khop, forward_2hop)
 from .adjacency import construct_adj, construct_test_adj
 

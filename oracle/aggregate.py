@@ -63,6 +63,18 @@ def maxpool_aggregator(self_vecs, neigh_vecs, mlp_weights, mlp_bias, neigh_weigh
     return act(out)
 
 
+def meanpool_aggregator(self_vecs, neigh_vecs, mlp_weights, mlp_bias, neigh_weights, self_weights,
+                        concat=False, act=relu):
+    """reference graphsage/aggregators.py:246-273: as max-pool with reduce_mean over the fanout."""
+    n, k, d = neigh_vecs.shape
+    h = dense(neigh_vecs.reshape(n * k, d), mlp_weights, mlp_bias, relu)
+    h = h.reshape(n, k, -1).mean(axis=1, dtype=h.dtype)                     # :262
+    from_neighs = h @ neigh_weights
+    from_self = self_vecs @ self_weights
+    out = np.concatenate([from_self, from_neighs], axis=1) if concat else from_self + from_neighs
+    return act(out)
+
+
 def l2_normalize(x, eps=1e-12):
     """tf.nn.l2_normalize(x, 1): x * rsqrt(max(sum(x^2), eps)) - reference graphsage/models.py:368."""
     ss = (x * x).sum(axis=1, keepdims=True, dtype=x.dtype)

@@ -23,7 +23,7 @@ import tf_shim  # noqa: E402
 tf = tf_shim.install()
 
 from graphsage.neigh_samplers import UniformNeighborSampler  # noqa: E402
-from graphsage.aggregators import MeanAggregator, GCNAggregator, MaxPoolingAggregator  # noqa: E402
+from graphsage.aggregators import MeanAggregator, GCNAggregator, MaxPoolingAggregator, MeanPoolingAggregator  # noqa: E402
 from graphsage.models import SampleAndAggregate, SAGEInfo  # noqa: E402
 from graphsage.minibatch import NodeMinibatchIterator  # noqa: E402
 from graphsage.inits import glorot  # noqa: E402
@@ -181,8 +181,29 @@ def golden_adjacency():
          max_degree=md, adj=it.adj.astype(np.int32), deg=it.deg, test_adj=it.test_adj.astype(np.int32))
 
 
+def golden_meanpool():
+    """MeanPoolingAggregator (reference aggregators.py:197-273), generated separately so the older fixtures keep their bytes."""
+    rs2 = np.random.RandomState(21)
+    n, k, din, dout = 29, 7, 40, 16
+    selfv = rs2.randn(n, din).astype(np.float32)
+    neigh = rs2.randn(n, k, din).astype(np.float32)
+    out = {"self": selfv, "neigh": neigh}
+    for concat in (False, True):
+        agg = MeanPoolingAggregator(din, dout, concat=concat)
+        tag = "c%d" % concat
+        agg.mlp_layers[0].vars["bias"] = agg.mlp_layers[0].vars["bias"] + rs2.randn(agg.hidden_dim).astype(np.float32) * 0.1
+        out[tag + "_nw"], out[tag + "_sw"] = agg.vars["neigh_weights"], agg.vars["self_weights"]
+        out[tag + "_mw"], out[tag + "_mb"] = agg.mlp_layers[0].vars["weights"], agg.mlp_layers[0].vars["bias"]
+        out[tag + "_out"] = agg((selfv, neigh))
+    save("meanpool", **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "meanpool":
+        golden_meanpool()
+        sys.exit(0)
     golden_sampler()
     golden_aggregators()
     golden_khop()
     golden_adjacency()
+    golden_meanpool()

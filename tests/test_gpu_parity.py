@@ -532,3 +532,37 @@ def test_pipelined_forward_matches_eager(gs):
     for i in range(5):
         assert torch.equal(outs[i], eager[i].cpu()), "pipelined step %d differs from eager step %d" % (i, i)
     pipe.close()
+
+
+# ---------------------------------------------------------------- mean-pool aggregator
+def test_meanpool_golden_and_fused(gs):
+    g = load_golden("meanpool")
+    s, n = dev(g["self"]), dev(g["neigh"])
+    gs.set_default_math("fp32")
+    for c in (0, 1):
+        agg = gs.MeanPoolingAggregator(40, 16, concat=bool(c))
+        assert agg.hidden_dim == 512 and agg.pool == "mean"
+        _inject(agg, neigh_weights=g["c%d_nw" % c], self_weights=g["c%d_sw" % c])
+        _inject(agg.mlp_layers[0], weights=g["c%d_mw" % c], bias=g["c%d_mb" % c])
+        assert rel_err(agg((s, n)).cpu().numpy(), g["c%d_out" % c]) < TOL
+    # K4 with the mean epilogue vs an fp64 reference on the same bf16 operands
+    rs = np.random.RandomState(6)
+    n_rows, K, hidden, n_groups, k = 3000, 602, 512, 777, 25
+    table = torch.zeros((n_rows, gs.ops.pad_cols(K)), dtype=torch.bfloat16, device="cuda")
+    table[:, :K] = dev(rs.randn(n_rows, K).astype(np.float32)).to(torch.bfloat16)
+    W = dev((rs.randn(K, hidden) / np.sqrt(K)).astype(np.float32))
+    bias = dev(rs.randn(hidden).astype(np.float32))
+    ids = rs.randint(0, n_rows, size=n_groups * k).astype(np.int32)
+    out = gs.ops.maxpool_mlp_fused(table[:, :K], n_groups, k, W, bias, gs.ops.PackedMlpWeights(), row_ids=dev(ids),
+                                   pool="mean")
+    rows = table[dev(ids).long(), :K].double()
+    ref = torch.relu(rows @ W.to(torch.bfloat16).double() + bias.double()).reshape(n_groups, k, hidden).mean(dim=1)
+    assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < 2e-5
+    # and through the model: aggregator_type="meanpool"
+    gk = load_golden("khop")
+    sampler = gs.UniformNeighborSampler(dev(gk["adj"]), seed=3)
+    infos = [gs.SAGEInfo("node", sampler, 4, 8), gs.SAGEInfo("node", sampler, 2, 8)]
+    m = gs.SampleAndAggregate({"batch_size": 9, "dropout": 0.}, dev(gk["feats"]), dev(gk["adj"]), None, infos,
+                              concat=True, aggregator_type="meanpool")
+    emb = m.export_embeddings(np.arange(20), batch_size=9)
+    assert emb.shape == (20, 16) and np.allclose(np.linalg.norm(emb, axis=1), 1.0, atol=1e-5)

@@ -156,3 +156,11 @@ def test_unigram_sampler_oracle_distribution():
     p = np.bincount(big, minlength=1000) / 200000.0
     q = deg ** 0.75 / (deg ** 0.75).sum()
     assert np.abs(p - q).max() < 1e-3
+
+
+def test_meanpool_matches_reference_under_shim():
+    g = load_golden("meanpool")
+    for c in (0, 1):
+        y = oracle.meanpool_aggregator(g["self"], g["neigh"], g["c%d_mw" % c], g["c%d_mb" % c], g["c%d_nw" % c],
+                                       g["c%d_sw" % c], concat=bool(c))
+        assert rel_err(y, g["c%d_out" % c]) < 1e-6
