@@ -365,7 +365,7 @@ def main():
         avg_ms = rep["gather_kernel_ms"]
         achieved = GATHER_BYTES / (avg_ms * 1e-3) / 1e9
         traffic = None                      # dram__bytes_read + dram__bytes_write of this kernel, committed ncu capture
-        prof = os.path.join(ROOT, "profiles", "ncu_gather_r01_summary.txt")
+        prof = os.path.join(ROOT, "profiles", "ncu_gather_r01_final_summary.txt")
         if os.path.exists(prof):
             vals = {}
             for line in open(prof):
@@ -378,7 +378,7 @@ def main():
                 traffic = sum(vals.values())
         roof = {"bound": "hbm", "kernel": "gather_mean (layer 0, hops 0+1)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": "profiles/ncu_gather_r01_summary.txt (ncu --set full, one launch; bytes)", "peak_source": peak_src,
+                "traffic_source": "profiles/ncu_gather_r01_final_summary.txt (ncu --set full, one launch; bytes)", "peak_source": peak_src,
                 "avg_kernel_ms": avg_ms, "algorithmic_bytes_per_launch": GATHER_BYTES,
                 "kernel_share_of_step": avg_ms / rep["ms_probe_step"],
                 "measured_in": "second timed pass of the same steps with this kernel isolated in its own CUDA-graph node "

@@ -484,7 +484,7 @@ int32_t gs_gather_rows(const void* feats, int32_t dtype, int64_t n_rows, int32_t
   const int row_bytes = ((F * es + 15) / 16) * 16;
   const bool tma_ok = gs::aligned16(feats) && gs::aligned16(out) && (pitch * es) % 16 == 0 && (out_pitch * es) % 16 == 0 &&
                       row_bytes <= pitch * es && row_bytes <= out_pitch * es && row_bytes * 32 <= 200 * 1024;
-  if (tma_ok && gs::tuning("gather_variant", 1) == 1) {
+  if (tma_ok && gs::tuning("gather_variant", 2) != 0) {
     size_t smem = (size_t)row_bytes * 32;
     static bool attr_set = false;
     if (!attr_set) {
@@ -549,7 +549,7 @@ int32_t gs_gather_mean(const void* src, int32_t dtype, int64_t n_src_rows, int32
   const int ncol4 = (int)(out_pitch / 4);
   const int row_bytes = ((F + 3) / 4) * 16;
   const size_t smem = (size_t)row_bytes * (kmax + 1);
-  const int variant = gs::tuning("gather_variant", 1);
+  const int variant = gs::tuning("gather_variant", 2);   // 2: grouped double-buffered TMA (default), 1: whole-node TMA, 0: LDG
   if (variant == 2 && ncol4 <= 2 * 160) {
     static bool attr2_set = false;
     if (!attr2_set) {

@@ -115,7 +115,7 @@ def test_gather_rows_exact(gs, variant, F):
         ob = gs.ops.gather_rows(bf, dev(ids))
         assert torch.equal(ob, bf[dev(ids).long()])
     finally:
-        gs._lib.set_tuning("gather_variant", 1)
+        gs._lib.set_tuning("gather_variant", 2)
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2])
@@ -152,7 +152,7 @@ def test_gather_mean_matches_numpy(gs, variant):
         _, m = gs.ops.gather_mean(dev(H), [gs.ops.Seg(n0, k0, self_row0=0, neigh_row0=n0)], want_self=False)
         assert rel_err(m.cpu().numpy()[:, :256], H[n0:].reshape(n0, k0, 256).mean(1)) < 1e-5
     finally:
-        gs._lib.set_tuning("gather_variant", 1)
+        gs._lib.set_tuning("gather_variant", 2)
 
 
 def test_gather_mean_odd_width_scalar_path(gs):

@@ -69,7 +69,7 @@ for variant in (2, 1, 0):
         med, mn = timeit(run)
         res["gather_mean_v%d_cps%d" % (variant, cps)] = {"ms_median": med, "ms_min": mn, "alg_GBps": gbytes / med / 1e6}
         print("gather_mean variant", variant, "ctas/sm", cps, "median ms", med, "alg GB/s", gbytes / med / 1e6, flush=True)
-gs._lib.set_tuning("gather_variant", 1)
+gs._lib.set_tuning("gather_variant", 2)
 gs._lib.set_tuning("gather_ctas_per_sm", 8)
 
 allids = [torch.cat(s) for s in sets]
