@@ -74,6 +74,7 @@ __host__ __device__ inline uint32_t philox_draw(uint64_t seed, uint64_t counter,
 constexpr uint32_t kStreamPadded = 0u;
 constexpr uint32_t kStreamCsr = 0x40000000u;
 constexpr uint32_t kStreamUnigram = 0x20000000u;
+constexpr uint32_t kStreamBuild = 0x10000000u;
 
 // ---- PTX wrappers (mbarrier / bulk copy) ---------------------------------------------------
 #ifdef __CUDACC__

@@ -179,6 +179,51 @@ __global__ void __launch_bounds__(128) sample_unigram_kernel(const double* __res
   out[j] = (int32_t)lo;
 }
 
+// padded adjacency from CSR, one warp per node (start-up time, not per batch)
+__global__ void __launch_bounds__(256) build_padded_adj_kernel(const int64_t* __restrict__ indptr,
+                                                               const int32_t* __restrict__ indices, int64_t n_nodes,
+                                                               int32_t max_deg, const uint8_t* __restrict__ skip,
+                                                               uint64_t seed, uint64_t counter, int32_t* __restrict__ adj,
+                                                               float* __restrict__ deg_out) {
+  __shared__ int32_t sel[8][kMaxDegSmem];            // Floyd's selected positions, one row per warp
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + w;
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t u = warp; u <= n_nodes; u += nwarps) {
+    int32_t* row = adj + u * max_deg;
+    int64_t start = 0, deg = 0;
+    if (u < n_nodes && !(skip && skip[u])) {
+      start = indptr[u];
+      deg = indptr[u + 1] - start;
+    }
+    if (u < n_nodes && deg_out && lane == 0) deg_out[u] = (float)deg;
+    if (deg == 0) {
+      for (int j = lane; j < max_deg; j += 32) row[j] = (int32_t)n_nodes;
+    } else if (deg == max_deg) {
+      for (int j = lane; j < max_deg; j += 32) row[j] = indices[start + j];
+    } else if (deg < max_deg) {
+      for (int j = lane; j < max_deg; j += 32) {
+        const uint32_t r = philox_draw(seed, counter, (uint32_t)u, kStreamBuild, j);
+        row[j] = indices[start + (int64_t)mulhi32(r, (uint32_t)deg)];
+      }
+    } else {
+      // Floyd: step j draws t in [0, deg - max_deg + j]; a repeat is replaced by the upper bound itself
+      for (int j = 0; j < max_deg; ++j) {
+        const int64_t m = deg - max_deg + j;
+        const uint32_t r = philox_draw(seed, counter, (uint32_t)u, kStreamBuild, j);   // same value in every lane
+        const int32_t t = (int32_t)mulhi32(r, (uint32_t)(m + 1));
+        bool dup = false;
+        for (int q = lane; q < j; q += 32) dup |= (sel[w][q] == t);
+        dup = __any_sync(0xffffffffu, dup);
+        if (lane == 0) sel[w][j] = dup ? (int32_t)m : t;
+        __syncwarp();
+      }
+      for (int j = lane; j < max_deg; j += 32) row[j] = indices[start + sel[w][j]];
+      __syncwarp();
+    }
+  }
+}
+
 }  // namespace gs
 
 extern "C" {
@@ -231,6 +276,18 @@ int32_t gs_sample_padded_khop(const int32_t* adj, int64_t n_rows, int32_t max_de
   gs::sample_padded_khop_kernel<<<(unsigned)blocks, 512, 0, (cudaStream_t)stream>>>(adj, n_rows, max_deg, seeds, kp, seed,
                                                                                     counter, counter_dev);
   return gs::launch_check("sample_padded_khop_kernel");
+}
+
+int32_t gs_build_padded_adj(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, int32_t max_deg,
+                            const uint8_t* skip, uint64_t seed, uint64_t counter, int32_t* adj, float* deg, void* stream) {
+  GS_REQUIRE(indptr && indices && adj && n_nodes >= 0, "gs_build_padded_adj: NULL pointer / bad size");
+  GS_REQUIRE(max_deg >= 1 && max_deg <= gs::kMaxDegSmem, "gs_build_padded_adj: need 1 <= max_deg <= %d", gs::kMaxDegSmem);
+  int64_t blocks = (n_nodes + 1 + 7) / 8;
+  int64_t cap = (int64_t)gs::sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  gs::build_padded_adj_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(indptr, indices, n_nodes, max_deg, skip,
+                                                                                   seed, counter, adj, deg);
+  return gs::launch_check("build_padded_adj_kernel");
 }
 
 int32_t gs_sample_unigram(const double* cdf, int64_t n, int32_t num_sampled, uint64_t seed, uint64_t counter,

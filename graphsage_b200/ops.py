@@ -85,6 +85,23 @@ def sample_padded_khop(adj, seeds, fanouts, seed, counter, counter_dev=None):
     return outs
 
 
+def build_padded_adj(indptr, indices, max_degree, seed=123, counter=0, skip=None):
+    """Padded adjacency [N+1, max_degree] (+ degree vector) from CSR on the device - the sampler's input contract,
+    reference graphsage/minibatch.py:227-259.  skip: optional bool/uint8 [N] (val/test nodes keep all-N rows)."""
+    require_cuda(indptr, indices, skip)
+    if indptr.dtype != torch.int64:
+        raise TypeError("indptr must be int64")
+    indices = _i32(indices, "indices")
+    n = indptr.numel() - 1
+    adj = torch.empty((n + 1, max_degree), dtype=torch.int32, device=indptr.device)
+    deg = torch.empty((n,), dtype=torch.float32, device=indptr.device)
+    sk = None if skip is None else skip.to(torch.uint8).contiguous()
+    check(lib().gs_build_padded_adj(ptr(indptr), ptr(indices), n, max_degree, ptr(sk), seed & _U64, counter & _U64,
+                                    ptr(adj), ptr(deg), stream_ptr()))
+    _launched(1)
+    return adj, deg
+
+
 def sample_unigram(cdf, num_sampled, seed, counter, counter_dev=None):
     """tf.nn.fixed_unigram_candidate_sampler(unique=False) - reference graphsage/models.py:336-343.
     cdf: float64 CUDA tensor, inclusive prefix sum of the (distorted) unigram weights."""

@@ -93,6 +93,20 @@ int32_t gs_sample_csr(const int64_t* indptr, const int32_t* indices, int64_t n_n
 int32_t gs_sample_unigram(const double* cdf, int64_t n, int32_t num_sampled, uint64_t seed, uint64_t counter,
                           const uint64_t* counter_dev, int32_t* out, void* stream);
 
+/* Device-side construction of the padded adjacency table from CSR (the sampler's input contract, reference
+ * graphsage/minibatch.py:227-259).  adj is [n_nodes + 1, max_deg] int32:
+ *   row n_nodes (dummy) and rows of skipped nodes (skip[u] != 0: val/test nodes, minibatch.py:232-233) or of
+ *   nodes without neighbours = n_nodes;  deg == max_deg: the neighbours in CSR order;
+ *   deg <  max_deg: max_deg draws WITH replacement (minibatch.py:242-243);
+ *   deg >  max_deg: max_deg distinct neighbours (Floyd's algorithm; minibatch.py:240-241).
+ * Draw j of node u is word j&3 of Philox block (counter, c2 = u, build tag + j>>2)  (oracle/adjacency.py:
+ * build_padded_adj; the reference's numpy RandomState stream is reproduced by the HOST builder
+ * graphsage_b200/minibatch.py instead).  max_deg <= 1024.  deg (float32 [n_nodes], may be NULL) receives the
+ * neighbour counts (minibatch.py:237). */
+int32_t gs_build_padded_adj(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, int32_t max_deg,
+                            const uint8_t* skip, uint64_t seed, uint64_t counter, int32_t* adj, float* deg,
+                            void* stream);
+
 /* host helper: the first k entries of pi for (seed, counter) - what the kernel computes */
 int32_t gs_perm_prefix_host(uint64_t seed, uint64_t counter, int32_t max_deg, int32_t k,
                             int32_t* out_host);

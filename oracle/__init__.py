@@ -26,6 +26,6 @@ from .sampler import (perm_prefix, sample_padded, sample_csr, sample_unigram,
 from .aggregate import (gather_rows, mean_aggregator, gcn_aggregator,
                         maxpool_aggregator, meanpool_aggregator, dense, l2_normalize, glorot_range,
                         sample_khop, aggregate_khop, forward_2hop)
-from .adjacency import construct_adj, construct_test_adj
+from .adjacency import construct_adj, construct_test_adj, build_padded_adj
 
 __all__ = [n for n in dir() if not n.startswith("_")]

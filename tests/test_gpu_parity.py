@@ -566,3 +566,25 @@ def test_meanpool_golden_and_fused(gs):
                               concat=True, aggregator_type="meanpool")
     emb = m.export_embeddings(np.arange(20), batch_size=9)
     assert emb.shape == (20, 16) and np.allclose(np.linalg.norm(emb, axis=1), 1.0, atol=1e-5)
+
+
+# ---------------------------------------------------------------- device-side padded adjacency
+def test_build_padded_adj_bit_exact(gs):
+    from graphsage_b200.synthetic import community_graph_csr
+    indptr, indices, comm = community_graph_csr(3000, n_comm=5, mean_deg=20, seed=4)
+    rs = np.random.RandomState(1)
+    skip = rs.rand(3000) < 0.1
+    for md in (16, 25, 128):
+        adj, deg = gs.ops.build_padded_adj(dev(indptr), dev(indices), md, seed=123, counter=3, skip=dev(skip))
+        ref_adj, ref_deg = oracle.build_padded_adj(indptr, indices, md, 123, 3, skip=skip)
+        np.testing.assert_array_equal(adj.cpu().numpy(), ref_adj)
+        np.testing.assert_array_equal(deg.cpu().numpy(), ref_deg)
+        a = adj.cpu().numpy()
+        assert (a[3000] == 3000).all() and (a[np.nonzero(skip)[0]] == 3000).all()
+        d = np.diff(indptr)
+        for u in np.nonzero((d > md) & ~skip)[0][:50]:
+            assert len(set(a[u].tolist())) == md                       # without replacement
+            assert set(a[u].tolist()) <= set(indices[indptr[u]:indptr[u + 1]].tolist())
+    # the table feeds the sampler directly
+    out = gs.ops.sample_padded(adj, dev(np.arange(100, dtype=np.int32)), 10, 1, 1)
+    assert out.shape == (100, 10)

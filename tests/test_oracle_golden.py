@@ -164,3 +164,17 @@ def test_meanpool_matches_reference_under_shim():
         y = oracle.meanpool_aggregator(g["self"], g["neigh"], g["c%d_mw" % c], g["c%d_mb" % c], g["c%d_nw" % c],
                                        g["c%d_sw" % c], concat=bool(c))
         assert rel_err(y, g["c%d_out" % c]) < 1e-6
+
+
+def test_build_padded_adj_oracle_properties():
+    rs = np.random.RandomState(3)
+    n, md = 200, 8
+    deg = rs.randint(0, 30, size=n)
+    deg[:3] = [0, md, md + 5]
+    indptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    indices = np.concatenate([rs.choice(n, d, replace=False) for d in deg]).astype(np.int32)
+    adj, d = oracle.build_padded_adj(indptr, indices, md, 5, 0)
+    assert adj.shape == (n + 1, md) and (adj[n] == n).all() and (adj[0] == n).all()
+    np.testing.assert_array_equal(adj[1], indices[indptr[1]:indptr[2]])
+    assert len(set(adj[2].tolist())) == md and set(adj[2].tolist()) <= set(indices[indptr[2]:indptr[3]].tolist())
+    np.testing.assert_array_equal(d, deg.astype(np.float32))
