@@ -45,6 +45,7 @@ struct TcParams {
   float* out;
   int64_t ldo;
   int32_t tiles_n0;    // number of N tiles of part 0 (CONCAT tile -> part mapping)
+  int32_t issue_elect; // 1: warp-uniform elect.sync issue (default), 0: one thread inside `if (lane == 0)`
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -376,13 +377,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __gri
       if (lane == 0 && it == 1) dbg_stamp(10);
       if (lane == 0 && it == 8) dbg_stamp(11);
       if (lane == 0 && it == total_it - 1) dbg_stamp(12);
-      if (lane == 0) {
-        const uint32_t a_base = smem_u32(smem + (size_t)s * C::IMG_BYTES);
-        const uint32_t b_base = smem_u32(smem + C::B_OFF + (size_t)sb * C::IMG_BYTES);
-        const uint64_t a_hi = make_smem_desc(a_base), b_hi = make_smem_desc(b_base);
+      const uint32_t a_base = smem_u32(smem + (size_t)s * C::IMG_BYTES);
+      const uint32_t b_base = smem_u32(smem + C::B_OFF + (size_t)sb * C::IMG_BYTES);
+      const uint64_t a_hi = make_smem_desc(a_base), b_hi = make_smem_desc(b_base);
+      if (prm.issue_elect) {
+        // whole warp, uniform operands, elect.sync on the instruction (tc_common.cuh: umma_ss_elect)
 #pragma unroll
         for (int k = 0; k < C::BK / C::UK; ++k) {
           const uint64_t koff = (uint64_t)((k * 32) >> 4);          // 32 B per UMMA K step inside the swizzle atom
+          const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+          umma_ss_elect<MODE == 2>(tmem_acc, a_hi + koff, b_hi + koff, idesc, acc);
+          if constexpr (MODE == 0) {
+            const uint64_t a_lo = make_smem_desc(a_base + TC_TILE_BYTES), b_lo = make_smem_desc(b_base + TC_TILE_BYTES);
+            umma_ss_elect<false>(tmem_acc, a_hi + koff, b_lo + koff, idesc, 1u);
+            umma_ss_elect<false>(tmem_acc, a_lo + koff, b_hi + koff, idesc, 1u);
+          }
+        }
+        umma_commit_elect(&empty_a[s]);                                // A stage and B slot reusable once these MMAs retire
+        umma_commit_elect(&empty_b[sb]);
+        if (it == total_it - 1) umma_commit_elect(&accum_bar);         // accumulator complete
+        if (lane == 0 && it == total_it - 1) dbg_stamp(13);
+      } else if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < C::BK / C::UK; ++k) {
+          const uint64_t koff = (uint64_t)((k * 32) >> 4);
           const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
           umma_ss<MODE == 2>(tmem_acc, a_hi + koff, b_hi + koff, idesc, acc);
           if constexpr (MODE == 0) {
@@ -391,9 +409,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __gri
             umma_ss<false>(tmem_acc, a_lo + koff, b_hi + koff, idesc, 1u);
           }
         }
-        umma_commit(&empty_a[s]);                                    // A stage and B slot reusable once these MMAs retire
+        umma_commit(&empty_a[s]);
         umma_commit(&empty_b[sb]);
-        if (it == total_it - 1) umma_commit(&accum_bar);             // accumulator complete
+        if (it == total_it - 1) umma_commit(&accum_bar);
         if (it == total_it - 1) dbg_stamp(13);
       }
       __syncwarp();
@@ -447,6 +465,7 @@ static void fill_parts(TcParams& prm, int64_t M, const gs_gemm_part* parts, int3
     off += (int64_t)P.kblocks * P.ntiles * nimg * TC_TILE_BYTES;
   }
   prm.tiles_n0 = prm.p[0].ntiles;
+  prm.issue_elect = tuning("mma_issue", 1) != 0;
 }
 
 int64_t sage_gemm_tc_workspace(int64_t M, const gs_gemm_part* parts, int32_t n_parts, int32_t math) {

@@ -47,6 +47,7 @@ struct MpParams {
   int32_t pool_mean;            // 0: max over the fanout (MaxPoolingAggregator), 1: mean (MeanPoolingAggregator)
   float* out;                   // [n_groups, hidden]
   int64_t ldo;
+  int32_t issue_elect;          // 1: warp-uniform elect.sync issue (default), 0: one thread inside `if (lane == 0)`
 };
 
 // byte offset of 16-byte chunk c (0..3) of row r inside a K-major SWIZZLE_64B image (Swizzle<2,4,3>: address bits
@@ -209,11 +210,20 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
         const int s = it % MP_SA;
         mbar_wait(&full_a[s], (it / MP_SA) & 1u);
         tc_fence_after();
-        if (lane == 0) {
-          const uint64_t adesc = make_smem_desc64(smem_u32(a_ring + (size_t)s * MP_IMG));
-          const uint64_t bdesc = make_smem_desc64(smem_u32(b_res + (size_t)kb * MP_IMG));
+        const uint64_t adesc = make_smem_desc64(smem_u32(a_ring + (size_t)s * MP_IMG));
+        const uint64_t bdesc = make_smem_desc64(smem_u32(b_res + (size_t)kb * MP_IMG));
+        if (prm.issue_elect) {
+          // whole warp, uniform operands, elect.sync on the instruction (tc_common.cuh: umma_ss_elect)
 #pragma unroll
           for (int k2 = 0; k2 < 2; ++k2)            // two K = 16 steps per 32-column K-block (32 B apart inside the atom)
+            umma_ss_elect<true>(tmem_acc, adesc + (uint64_t)(k2 * 2), bdesc + (uint64_t)(k2 * 2), idesc,
+                                (kb > 0 || k2 > 0) ? 1u : 0u);
+          umma_commit_elect(&empty_a[s]);
+          if (kb == kblocks - 1) umma_commit_elect(&acc_full[buf]);
+          if (lane == 0 && kb == kblocks - 1) mp_stamp(tcount, 4);
+        } else if (lane == 0) {
+#pragma unroll
+          for (int k2 = 0; k2 < 2; ++k2)
             umma_ss<true>(tmem_acc, adesc + (uint64_t)(k2 * 2), bdesc + (uint64_t)(k2 * 2), idesc, (kb > 0 || k2 > 0) ? 1u : 0u);
           umma_commit(&empty_a[s]);
           if (kb == kblocks - 1) umma_commit(&acc_full[buf]);
@@ -357,6 +367,7 @@ static int32_t pool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K,
   prm.hidden = hidden; prm.n_slices = hidden / 128;
   prm.wimg = (const unsigned char*)packed_weights; prm.bias = bias; prm.out = out; prm.ldo = ldo;
   prm.pool_mean = pool_mean;
+  prm.issue_elect = gs::tuning("mma_issue", 1) != 0;
   static bool attr_set = false;
   if (!attr_set) {
     GS_CUDA(cudaFuncSetAttribute(gs::maxpool_mlp_kernel<7, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs::MP_SMEM));

@@ -48,6 +48,37 @@ __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_
   }
 }
 
+
+// Warp-uniform issue.  The WHOLE warp executes these with warp-uniform operands; only the instruction is predicated on
+// elect.sync.  ptxas then keeps the descriptors in uniform registers and emits UTCHMMA / UTCBAR back to back.  Issuing
+// from inside `if (lane == 0) { ... }` instead makes it wrap every tcgen05 instruction in an R2UR + ELECT/BRA.U.ANY
+// waterfall: measured 176 cycles per MMA (any N <= 256) against the tensor pipe's 64 (N = 128) / 128 (N = 256) floor,
+// which this form reaches (tools/mma_rate.py, csrc/probe_tc.cu).  elect.sync picks the same leader for the same
+// member mask, so a commit issued this way tracks the MMAs issued this way.
+template <bool kBf16>
+__device__ __forceinline__ void umma_ss_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  if constexpr (kBf16) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane base + t)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

@@ -1,0 +1,57 @@
+"""Developer check: tensor-core kernels (K3 GEMM, K4 pooled MLP) - parity tests, then timings for both MMA issue forms
+(tuning mma_issue = 1: warp-uniform elect.sync issue, 0: one thread inside `if (lane == 0)`)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.chdir(ROOT)
+import numpy as np  # noqa: E402
+import pytest  # noqa: E402
+import torch  # noqa: E402
+
+rc = pytest.main(["tests/test_gpu_parity.py", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider", "-k",
+                  "aggregators_golden or khop_golden or sage_gemm_math or maxpool or meanpool or small_layer or full_size_forward"])
+print("PYTEST_RC", int(rc), flush=True)
+
+import graphsage_b200 as gs  # noqa: E402
+from graphsage_b200 import ops  # noqa: E402
+
+lib = gs._lib.lib()
+dev = torch.device("cuda")
+
+
+def timeit(fn, n=40):
+    for _ in range(5):
+        fn()
+    evs = []
+    for _ in range(n):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    return float(np.median([a.elapsed_time(b) for a, b in evs])) * 1e3
+
+
+M, F = 5632, 602
+P = ops.pad_cols(F)
+xs, xm = torch.randn((M, P), device=dev), torch.randn((M, P), device=dev)
+Ws, Wn = torch.randn(F, 128, device=dev), torch.randn(F, 128, device=dev)
+B, H = 512, 512
+n_rows = 232966
+table = torch.randn((n_rows, P), device=dev).to(torch.bfloat16)
+ids = torch.randint(0, n_rows - 1, (B * 10 * 25,), device=dev, dtype=torch.int32)
+Wm = torch.randn(F, H, device=dev) / 25.0
+bm = torch.randn(H, device=dev) * 0.1
+pk = ops.PackedMlpWeights()
+for flag in (1, 0):
+    lib.gs_set_tuning(b"mma_issue", flag)
+    for math in ("tf32x3", "bf16"):
+        packed = ops.PackedWeights()
+        code = gs.aggregators._MATH_NAMES[math]
+        t = timeit(lambda: ops.sage_gemm([(xs, F, Ws), (xm, F, Wn)], combine=ops.COMBINE_CONCAT, act=ops.ACT_RELU, math=code,
+                                         packed=packed))
+        print("mma_issue=%d  K3 gemm [5632 x (602+602)] -> 256 %s: %.1f us" % (flag, math, t), flush=True)
+    t = timeit(lambda: ops.maxpool_mlp_fused(table[:, :F], B * 10, 25, Wm, bm, pk, row_ids=ids), n=20)
+    print("mma_issue=%d  K4 maxpool hop2 (B=512, hidden 512): %.1f us  %.1f TFLOP/s" % (flag, t, 2.0 * B * 250 * F * H / t / 1e6), flush=True)
+lib.gs_set_tuning(b"mma_issue", 1)
