@@ -4,7 +4,7 @@ williamleif/GraphSAGE.  `import graphsage_b200 as graphsage` is the intended dro
 
 All compute goes through libgraphsage_b200.so (include/graphsage_b200.h); there is no CPU fallback.
 """
-from . import _lib, aggregators, inits, layers, minibatch, models, neigh_samplers, ops  # noqa: F401
+from . import _lib, aggregators, graph, inits, layers, minibatch, models, neigh_samplers, ops, utils  # noqa: F401
 from .aggregators import (GCNAggregator, MaxPoolingAggregator, MeanAggregator, MeanPoolingAggregator,  # noqa: F401
                           set_default_math)
 from .layers import Dense, Layer, identity, relu  # noqa: F401

@@ -198,12 +198,112 @@ def golden_meanpool():
     save("meanpool", **out)
 
 
+def iterator_fixture_graph(seed=31, n=90):
+    """Deterministic small graph with val/test annotations, isolated nodes, a node whose edges all lead to val/test nodes,
+    and degrees on both sides of max_degree.  Node ids are ints (so that CPython's set order is reproducible)."""
+    from graphsage_b200.graph import Graph
+    r = np.random.RandomState(seed)
+    G = Graph()
+    ids = [int(i) for i in r.permutation(n) + 100]            # node ids 100..189, inserted in shuffled order
+    for u in ids:
+        G.add_node(u, val=bool(r.rand() < 0.12), test=bool(r.rand() < 0.15))
+    for u in ids:
+        if G.node[u]["val"] and G.node[u]["test"]:
+            G.node[u]["test"] = False
+    for u in ids[:-4]:                                           # the last four stay isolated
+        for v in r.choice(ids[:-4], size=[1, 2, 5, 9, 14][r.randint(5)], replace=False):
+            if int(v) != u:
+                G.add_edge(u, int(v))
+    for u, v in G.edges():
+        a, b = G.node[u], G.node[v]
+        G[u][v]["train_removed"] = bool(a["val"] or b["val"] or a["test"] or b["test"])
+    id2idx = {u: i for i, u in enumerate(sorted(ids))}
+    return G, id2idx
+
+
+def golden_iterators():
+    """NodeMinibatchIterator / EdgeMinibatchIterator (reference minibatch.py) driven over graphsage_b200.graph.Graph."""
+    from graphsage.minibatch import EdgeMinibatchIterator
+    G, id2idx = iterator_fixture_graph()
+    ph = {k: k for k in ("batch_size", "batch", "labels", "batch1", "batch2")}
+    out = {}
+    # ---- node iterator, integer class labels
+    lab = {u: int(u % 4) for u in G.nodes()}
+    np.random.seed(123)
+    it = NodeMinibatchIterator(G, id2idx, ph, lab, 4, batch_size=7, max_degree=6)
+    out.update(n_adj=it.adj.astype(np.int32), n_deg=it.deg, n_test_adj=it.test_adj.astype(np.int32),
+               n_train_nodes=np.array(it.train_nodes), n_val_nodes=np.array(it.val_nodes), n_test_nodes=np.array(it.test_nodes),
+               n_num_batches=it.num_training_batches())
+    f, l = it.next_minibatch_feed_dict()
+    out.update(n_b0=np.array(f["batch"]), n_l0=l, n_bs0=f["batch_size"])
+    f, l = it.next_minibatch_feed_dict()
+    out.update(n_b1=np.array(f["batch"]), n_l1=l)
+    f, l = it.node_val_feed_dict(size=5)
+    out.update(n_val5=np.array(f["batch"]), n_val5_labels=l)
+    f, l = it.node_val_feed_dict(test=True)
+    out.update(n_test_all=np.array(f["batch"]))
+    f, l, done, sub = it.incremental_node_val_feed_dict(4, 1)
+    out.update(n_inc=np.array(f["batch"]), n_inc_done=done, n_inc_nodes=np.array(sub))
+    (f, l), done, sub = it.incremental_embed_feed_dict(8, 2)
+    out.update(n_emb=np.array(f["batch"]), n_emb_done=done)
+    it.shuffle()
+    f, l = it.next_minibatch_feed_dict()
+    out.update(n_shuf_b0=np.array(f["batch"]), n_shuf_train=np.array(it.train_nodes))
+    n = 0
+    while not it.end():
+        it.next_minibatch_feed_dict()
+        n += 1
+    out.update(n_batches_to_end=n)
+    # ---- node iterator, multi-hot list labels
+    lab2 = {u: [int(u % 2), int(u % 3 == 0), 1] for u in G.nodes()}
+    np.random.seed(5)
+    it = NodeMinibatchIterator(G, id2idx, ph, lab2, 3, batch_size=5, max_degree=6)
+    f, l = it.next_minibatch_feed_dict()
+    out.update(n2_b0=np.array(f["batch"]), n2_l0=l)
+    # ---- edge iterator over graph edges
+    np.random.seed(123)
+    it = EdgeMinibatchIterator(G, id2idx, ph, batch_size=9, max_degree=6)
+    out.update(e_nodes=np.array(it.nodes), e_adj=it.adj.astype(np.int32), e_deg=it.deg, e_test_adj=it.test_adj.astype(np.int32),
+               e_train_edges=np.array(it.train_edges), e_val_edges=np.array(it.val_edges), e_num_batches=it.num_training_batches())
+    f = it.next_minibatch_feed_dict()
+    out.update(e_b1=np.array(f["batch1"]), e_b2=np.array(f["batch2"]), e_bs=f["batch_size"])
+    f = it.val_feed_dict(size=6)
+    out.update(e_val6_1=np.array(f["batch1"]), e_val6_2=np.array(f["batch2"]))
+    f, done, sub = it.incremental_val_feed_dict(5, 1)
+    out.update(e_inc1=np.array(f["batch1"]), e_inc2=np.array(f["batch2"]), e_inc_done=done)
+    f, done, sub = it.incremental_embed_feed_dict(10, 3)
+    out.update(e_emb1=np.array(f["batch1"]), e_emb_done=done)
+    tr, va = it.label_val()
+    out.update(e_label_train=np.array(tr), e_label_val=np.array(va))
+    it.shuffle()
+    f = it.next_minibatch_feed_dict()
+    out.update(e_shuf_b1=np.array(f["batch1"]), e_shuf_nodes=np.array(it.nodes))
+    # ---- edge iterator over context pairs (random-walk co-occurrences), n2v modes
+    r = np.random.RandomState(3)
+    nodes = G.nodes()
+    pairs = [(nodes[i], nodes[j]) for i, j in r.randint(0, len(nodes), size=(60, 2))]
+    np.random.seed(77)
+    it = EdgeMinibatchIterator(G, id2idx, ph, context_pairs=pairs, batch_size=9, max_degree=6)
+    out.update(c_pairs=np.array(pairs), c_train_edges=np.array(it.train_edges))
+    np.random.seed(78)
+    it = EdgeMinibatchIterator(G, id2idx, ph, context_pairs=pairs, batch_size=9, max_degree=6, n2v_retrain=True, fixed_n2v=True)
+    out.update(c_n2v_fixed=np.array(it.train_edges))
+    np.random.seed(79)
+    it = EdgeMinibatchIterator(G, id2idx, ph, context_pairs=pairs, batch_size=9, max_degree=6, n2v_retrain=True)
+    out.update(c_n2v=np.array(it.train_edges))
+    save("iterators", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "meanpool":
         golden_meanpool()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "iterators":
+        golden_iterators()
         sys.exit(0)
     golden_sampler()
     golden_aggregators()
     golden_khop()
     golden_adjacency()
     golden_meanpool()
+    golden_iterators()
