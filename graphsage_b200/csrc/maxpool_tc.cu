@@ -16,6 +16,8 @@
 //   warp  5    loads the resident weight slice (cp.async.bulk + mbarrier)
 //   warps 6-9  epilogue: tcgen05.ld -> + bias -> ReLU -> staged transpose in shared memory -> max over the k rows
 //              of each group -> coalesced store; overlaps the next tile's MMAs (second TMEM buffer)
+#include <cuda.h>   // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint (no libcuda link)
+
 #include "tc_common.cuh"
 
 namespace gs {
@@ -91,6 +93,137 @@ __device__ __forceinline__ void mp_stamp(uint32_t tcount, int slot) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     g_mp_dbg[tcount * 8 + slot] = t;
+  }
+}
+
+// ---- roles shared by the kernel variants (forced inline: one copy of the logic, no call overhead) ----
+
+// MMA issuer warp: waits for each A stage, issues the two K = 16 MMAs of the K-block against the resident weights,
+// commits the stage back to the producers and, after a tile's last K-block, the accumulator to the epilogue.
+template <int MP_SA>
+__device__ __forceinline__ void mp_mma_role(const MpParams& prm, int lane, int kblocks, int64_t tile0, int64_t tile_step,
+                                            uint32_t tmem_base, uint64_t* full_a, uint64_t* empty_a, uint64_t* acc_full,
+                                            uint64_t* acc_empty, uint64_t& b_full, unsigned char* a_ring,
+                                            unsigned char* b_res) {
+  // =============================== MMA issuer ===============================
+  constexpr uint32_t idesc = make_idesc(1u, TC_BM, TC_BN);          // bf16 x bf16 -> fp32
+  mbar_wait(&b_full, 0);
+  uint32_t it = 0, tcount = 0;
+  for (int64_t t = tile0; t < prm.n_tiles; t += tile_step, ++tcount) {
+    const uint32_t buf = tcount & 1u;
+    if (lane == 0) mp_stamp(tcount, 2);
+    mbar_wait(&acc_empty[buf], ((tcount >> 1) & 1u) ^ 1u);          // epilogue has drained this accumulator
+    tc_fence_after();
+    if (lane == 0) mp_stamp(tcount, 3);
+    const uint32_t tmem_acc = tmem_base + buf * 128u;
+    for (int kb = 0; kb < kblocks; ++kb, ++it) {
+      const int s = it % MP_SA;
+      mbar_wait(&full_a[s], (it / MP_SA) & 1u);
+      tc_fence_after();
+      const uint64_t adesc = make_smem_desc64(smem_u32(a_ring + (size_t)s * MP_IMG));
+      const uint64_t bdesc = make_smem_desc64(smem_u32(b_res + (size_t)kb * MP_IMG));
+      if (prm.issue_elect) {
+        // whole warp, uniform operands, elect.sync on the instruction (tc_common.cuh: umma_ss_elect)
+#pragma unroll
+        for (int k2 = 0; k2 < 2; ++k2)            // two K = 16 steps per 32-column K-block (32 B apart inside the atom)
+          umma_ss_elect<true>(tmem_acc, adesc + (uint64_t)(k2 * 2), bdesc + (uint64_t)(k2 * 2), idesc,
+                              (kb > 0 || k2 > 0) ? 1u : 0u);
+        umma_commit_elect(&empty_a[s]);
+        if (kb == kblocks - 1) umma_commit_elect(&acc_full[buf]);
+        if (lane == 0 && kb == kblocks - 1) mp_stamp(tcount, 4);
+      } else if (lane == 0) {
+#pragma unroll
+        for (int k2 = 0; k2 < 2; ++k2)
+          umma_ss<true>(tmem_acc, adesc + (uint64_t)(k2 * 2), bdesc + (uint64_t)(k2 * 2), idesc, (kb > 0 || k2 > 0) ? 1u : 0u);
+        umma_commit(&empty_a[s]);
+        if (kb == kblocks - 1) umma_commit(&acc_full[buf]);
+        if (kb == kblocks - 1) mp_stamp(tcount, 4);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// Weight loader warp: one bulk copy per K-block image of this CTA's slice, once.
+__device__ __forceinline__ void mp_weights_role(const MpParams& prm, int lane, int slice, int kblocks, uint64_t& b_full,
+                                                unsigned char* b_res) {
+  // =============================== resident weight slice ===============================
+  if (lane == 0) {
+    mbar_expect_tx(&b_full, (uint32_t)(kblocks * MP_IMG));
+    const unsigned char* src = prm.wimg + (int64_t)slice * kblocks * MP_IMG;
+    for (int kb = 0; kb < kblocks; ++kb)
+      bulk_g2s(b_res + (size_t)kb * MP_IMG, src + (int64_t)kb * MP_IMG, MP_IMG, &b_full);
+  }
+  __syncwarp();
+}
+
+// Epilogue (four consecutive warps; et = 0..127 is the thread's index among them).
+__device__ __forceinline__ void mp_epilogue_role(const MpParams& prm, int et, int warp, int lane, int slice, int64_t tile0,
+                                                 int64_t tile_step, uint32_t tmem_base, uint64_t* acc_full,
+                                                 uint64_t* acc_empty, float* stage, float* bias_s) {
+  // =============================== epilogue ===============================
+  const int q = warp & 3;                         // TMEM lane quarter of this warp (four consecutive warps cover 0..3)
+  const int row = q * 32 + lane;                  // tile row held by this thread
+  const int k = prm.k, G = prm.G;
+  bias_s[et] = prm.bias ? prm.bias[slice * 128 + et] : 0.f;     // this CTA's 128 bias values, once
+  named_bar_sync(1, 128);
+  uint32_t tcount = 0;
+  for (int64_t t = tile0; t < prm.n_tiles; t += tile_step, ++tcount) {
+    const uint32_t buf = tcount & 1u;
+    if (et == 0) mp_stamp(tcount, 5);
+    mbar_wait(&acc_full[buf], (tcount >> 1) & 1u);
+    tc_fence_after();
+    if (et == 0) mp_stamp(tcount, 6);
+    const uint32_t tmem_acc = tmem_base + buf * 128u + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int cb = 0; cb < 4; ++cb) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_acc + (uint32_t)(cb * 32), r);
+      tmem_ld_wait();
+      const int hcol0 = slice * 128 + cb * 32;
+      // raw accumulators go to the staging tile; bias and ReLU are applied AFTER the max
+      // (max_j relu(x_j + b) == relu(max_j x_j + b): b is per column, relu is monotone)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) stage[j * MP_STAGE_LD + row] = __uint_as_float(r[j]);
+      named_bar_sync(1, 128);
+      // thread = (column cc, group residue): max over each group's k consecutive rows, 8 independent
+      // shared loads per batch
+      {
+        const int cc = et & 31;
+        for (int g = et >> 5; g < G; g += 4) {
+          const int64_t gg = t * G + g;
+          if (gg < prm.n_groups) {
+            const float* p = stage + cc * MP_STAGE_LD + g * k;
+            const float b = bias_s[cb * 32 + cc];
+            float res;
+            if (prm.pool_mean) {
+              // mean-pool (reference aggregators.py:246-273): ReLU does not commute with the mean, so bias + ReLU
+              // are applied per element, summed in j order, divided by k
+              float sacc = 0.f;
+              for (int j = 0; j < k; ++j) sacc += fmaxf(p[j] + b, 0.f);
+              res = sacc / (float)k;
+            } else {
+              float m = -3.0e38f;
+              int j = 0;
+              for (; j + 8 <= k; j += 8) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = p[j + u];
+                m = fmaxf(m, fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7]))));
+              }
+              for (; j < k; ++j) m = fmaxf(m, p[j]);
+              res = fmaxf(m + b, 0.f);                                          // Dense bias + ReLU (commute with the max)
+            }
+            prm.out[gg * prm.ldo + hcol0 + cc] = res;
+          }
+        }
+      }
+      named_bar_sync(1, 128);
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    if (et == 0) mp_stamp(tcount, 7);
   }
 }
 
@@ -195,121 +328,139 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
       --pending;
     }
   } else if (warp == MP_PROD_WARPS) {
-    // =============================== MMA issuer ===============================
-    constexpr uint32_t idesc = make_idesc(1u, TC_BM, TC_BN);          // bf16 x bf16 -> fp32
-    mbar_wait(&b_full, 0);
-    uint32_t it = 0, tcount = 0;
-    for (int64_t t = tile0; t < prm.n_tiles; t += tile_step, ++tcount) {
-      const uint32_t buf = tcount & 1u;
-      if (lane == 0) mp_stamp(tcount, 2);
-      mbar_wait(&acc_empty[buf], ((tcount >> 1) & 1u) ^ 1u);          // epilogue has drained this accumulator
-      tc_fence_after();
-      if (lane == 0) mp_stamp(tcount, 3);
-      const uint32_t tmem_acc = tmem_base + buf * 128u;
-      for (int kb = 0; kb < kblocks; ++kb, ++it) {
-        const int s = it % MP_SA;
-        mbar_wait(&full_a[s], (it / MP_SA) & 1u);
-        tc_fence_after();
-        const uint64_t adesc = make_smem_desc64(smem_u32(a_ring + (size_t)s * MP_IMG));
-        const uint64_t bdesc = make_smem_desc64(smem_u32(b_res + (size_t)kb * MP_IMG));
-        if (prm.issue_elect) {
-          // whole warp, uniform operands, elect.sync on the instruction (tc_common.cuh: umma_ss_elect)
-#pragma unroll
-          for (int k2 = 0; k2 < 2; ++k2)            // two K = 16 steps per 32-column K-block (32 B apart inside the atom)
-            umma_ss_elect<true>(tmem_acc, adesc + (uint64_t)(k2 * 2), bdesc + (uint64_t)(k2 * 2), idesc,
-                                (kb > 0 || k2 > 0) ? 1u : 0u);
-          umma_commit_elect(&empty_a[s]);
-          if (kb == kblocks - 1) umma_commit_elect(&acc_full[buf]);
-          if (lane == 0 && kb == kblocks - 1) mp_stamp(tcount, 4);
-        } else if (lane == 0) {
-#pragma unroll
-          for (int k2 = 0; k2 < 2; ++k2)
-            umma_ss<true>(tmem_acc, adesc + (uint64_t)(k2 * 2), bdesc + (uint64_t)(k2 * 2), idesc, (kb > 0 || k2 > 0) ? 1u : 0u);
-          umma_commit(&empty_a[s]);
-          if (kb == kblocks - 1) umma_commit(&acc_full[buf]);
-          if (kb == kblocks - 1) mp_stamp(tcount, 4);
-        }
-        __syncwarp();
-      }
-    }
+    mp_mma_role<MP_SA>(prm, lane, kblocks, tile0, tile_step, tmem_base, full_a, empty_a, acc_full, acc_empty, b_full, a_ring,
+                       b_res);
   } else if (warp == MP_PROD_WARPS + 1) {
-    // =============================== resident weight slice ===============================
-    if (lane == 0) {
-      mbar_expect_tx(&b_full, (uint32_t)(kblocks * MP_IMG));
-      const unsigned char* src = prm.wimg + (int64_t)slice * kblocks * MP_IMG;
-      for (int kb = 0; kb < kblocks; ++kb)
-        bulk_g2s(b_res + (size_t)kb * MP_IMG, src + (int64_t)kb * MP_IMG, MP_IMG, &b_full);
-    }
-    __syncwarp();
+    mp_weights_role(prm, lane, slice, kblocks, b_full, b_res);
   } else {
-    // =============================== epilogue ===============================
-    const int et = threadIdx.x - (MP_PROD_WARPS + 2) * 32;   // 0..127
-    const int q = warp & 3;                         // TMEM lane quarter of this warp (four consecutive warps cover 0..3)
-    const int row = q * 32 + lane;                  // tile row held by this thread
-    const int k = prm.k, G = prm.G;
-    bias_s[et] = prm.bias ? prm.bias[slice * 128 + et] : 0.f;     // this CTA's 128 bias values, once
-    named_bar_sync(1, 128);
-    uint32_t tcount = 0;
-    for (int64_t t = tile0; t < prm.n_tiles; t += tile_step, ++tcount) {
-      const uint32_t buf = tcount & 1u;
-      if (et == 0) mp_stamp(tcount, 5);
-      mbar_wait(&acc_full[buf], (tcount >> 1) & 1u);
-      tc_fence_after();
-      if (et == 0) mp_stamp(tcount, 6);
-      const uint32_t tmem_acc = tmem_base + buf * 128u + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int cb = 0; cb < 4; ++cb) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_acc + (uint32_t)(cb * 32), r);
-        tmem_ld_wait();
-        const int hcol0 = slice * 128 + cb * 32;
-        // raw accumulators go to the staging tile; bias and ReLU are applied AFTER the max
-        // (max_j relu(x_j + b) == relu(max_j x_j + b): b is per column, relu is monotone)
-#pragma unroll
-        for (int j = 0; j < 32; ++j) stage[j * MP_STAGE_LD + row] = __uint_as_float(r[j]);
-        named_bar_sync(1, 128);
-        // thread = (column cc, group residue): max over each group's k consecutive rows, 8 independent
-        // shared loads per batch
-        {
-          const int cc = et & 31;
-          for (int g = et >> 5; g < G; g += 4) {
-            const int64_t gg = t * G + g;
-            if (gg < prm.n_groups) {
-              const float* p = stage + cc * MP_STAGE_LD + g * k;
-              const float b = bias_s[cb * 32 + cc];
-              float res;
-              if (prm.pool_mean) {
-                // mean-pool (reference aggregators.py:246-273): ReLU does not commute with the mean, so bias + ReLU
-                // are applied per element, summed in j order, divided by k
-                float sacc = 0.f;
-                for (int j = 0; j < k; ++j) sacc += fmaxf(p[j] + b, 0.f);
-                res = sacc / (float)k;
-              } else {
-                float m = -3.0e38f;
-                int j = 0;
-                for (; j + 8 <= k; j += 8) {
-                  float v[8];
-#pragma unroll
-                  for (int u = 0; u < 8; ++u) v[u] = p[j + u];
-                  m = fmaxf(m, fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7]))));
-                }
-                for (; j < k; ++j) m = fmaxf(m, p[j]);
-                res = fmaxf(m + b, 0.f);                                          // Dense bias + ReLU (commute with the max)
-              }
-              prm.out[gg * prm.ldo + hcol0 + cc] = res;
-            }
-          }
-        }
-        named_bar_sync(1, 128);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
-      if (et == 0) mp_stamp(tcount, 7);
-    }
+    mp_epilogue_role(prm, (int)threadIdx.x - (MP_PROD_WARPS + 2) * 32, warp, lane, slice, tile0, tile_step, tmem_base, acc_full,
+                     acc_empty, stage, bias_s);
   }
   __syncthreads();
   if (warp == MP_PROD_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Variant (GS_TUNING=k4_producer=1, not the default until measured): the gather-A producers use the TMA's row gather,
+// `cp.async.bulk.tensor.2d.tile::gather4` - one instruction fetches a 64-byte K-block segment of FOUR table rows named
+// by index and writes them, SWIZZLE_64B applied by the tensor map, straight into the UMMA stage; completion is the
+// stage's mbarrier transaction count.  No per-thread cp.async group waits, no generic->async proxy fence, no per-warp
+// arrive: what remains per stage is one empty-barrier wait, one expect_tx and one gather4 per lane (32 lanes x 4 rows =
+// the 128-row stage).  ptxas serialises the 32 lanes of an instruction with per-lane operands (ELECT waterfall), so
+// MP_G4_WARPS producer warps take K-blocks round-robin - each warp fills whole stages - to keep that latency off the
+// critical path.  Columns >= K and rows named n_rows (tile padding) are out of bounds for the tensor map: zero-filled.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int MP_G4_WARPS = 8;
+
+__device__ __forceinline__ void tma_gather4(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int col, int r0, int r1,
+                                            int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
+
+template <int MP_SA>
+__global__ void __launch_bounds__((MP_G4_WARPS + 6) * 32, 1)
+    maxpool_mlp_g4_kernel(const __grid_constant__ MpParams prm, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_a[MP_SA], empty_a[MP_SA], acc_full[2], acc_empty[2], b_full;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float bias_s[128];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* b_res = smem;                                        // resident weight slice
+  unsigned char* a_ring = smem + (MP_RING - MP_SA) * MP_IMG;
+  float* stage = reinterpret_cast<float*>(smem + MP_RING * MP_IMG);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x % prm.n_slices;
+  const int64_t tile0 = blockIdx.x / prm.n_slices, tile_step = gridDim.x / prm.n_slices;
+  const int kblocks = prm.kblocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MP_SA; ++s) {
+      mbar_init(&full_a[s], 1);           // the expect_tx arrive of the stage's producer warp (+ 8 KB of transactions)
+      mbar_init(&empty_a[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);        // one arrive per epilogue warp
+    }
+    mbar_init(&b_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == MP_G4_WARPS) {
+    tmem_alloc(&tmem_base_smem, 256);     // two 128-column fp32 accumulators
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp < MP_G4_WARPS) {
+    // =============================== gather-A producers (TMA gather4) ===============================
+    const int rows_valid = prm.G * prm.k;
+    const int64_t total_rows = prm.n_groups * prm.k;
+    const int64_t my_tiles = tile0 < prm.n_tiles ? (prm.n_tiles - tile0 + tile_step - 1) / tile_step : 0;
+    const int64_t total_it = my_tiles * kblocks;
+    const int oob_row = (int)prm.n_rows;            // out of bounds for the tensor map: the TMA writes zeros
+    int cur[4], nxt[4];                             // table rows of this lane's tile rows 4 lane .. 4 lane + 3
+    auto load_ids = [&](int64_t tl, int (&ids)[4]) {
+      const int64_t t = tile0 + tl * tile_step;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = 4 * lane + i;
+        const int64_t flat = t * rows_valid + r;    // index into the (group, j) row list
+        int64_t id = oob_row;
+        if (tl < my_tiles && r < rows_valid && flat < total_rows) {
+          id = prm.row_ids ? (int64_t)prm.row_ids[flat] : prm.row0 + flat;
+          if (id < 0 || id >= prm.n_rows) id = prm.n_rows - 1;
+        }
+        ids[i] = (int)id;
+      }
+    };
+    int64_t tl = 0;
+    int kb = warp;
+    while (kb >= kblocks) { kb -= kblocks; ++tl; }
+    load_ids(tl, cur);
+    load_ids(tl + 1, nxt);
+    for (int64_t it = warp; it < total_it; it += MP_G4_WARPS) {
+      const int s = (int)(it % MP_SA);
+      mbar_wait(&empty_a[s], ((uint32_t)(it / MP_SA) & 1u) ^ 1u);
+      if (lane == 0) mbar_expect_tx(&full_a[s], (uint32_t)MP_IMG);
+      __syncwarp();
+      tma_gather4(a_ring + (size_t)s * MP_IMG + lane * 256, &tmap, &full_a[s], kb * MP_KCOLS, cur[0], cur[1], cur[2], cur[3]);
+      // this warp's next K-block: MP_G4_WARPS further on, possibly in a later tile
+      kb += MP_G4_WARPS;
+      int adv = 0;
+      while (kb >= kblocks) { kb -= kblocks; ++adv; }
+      if (adv == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+        tl += 1;
+        load_ids(tl + 1, nxt);
+      } else if (adv > 1) {
+        tl += adv;
+        load_ids(tl, cur);
+        load_ids(tl + 1, nxt);
+      }
+    }
+  } else if (warp == MP_G4_WARPS) {
+    mp_mma_role<MP_SA>(prm, lane, kblocks, tile0, tile_step, tmem_base, full_a, empty_a, acc_full, acc_empty, b_full, a_ring,
+                       b_res);
+  } else if (warp == MP_G4_WARPS + 1) {
+    mp_weights_role(prm, lane, slice, kblocks, b_full, b_res);
+  } else {
+    mp_epilogue_role(prm, (int)threadIdx.x - (MP_G4_WARPS + 2) * 32, warp, lane, slice, tile0, tile_step, tmem_base, acc_full,
+                     acc_empty, stage, bias_s);
+  }
+  __syncthreads();
+  if (warp == MP_G4_WARPS) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
@@ -342,13 +493,43 @@ int32_t gs_maxpool_mlp_pack(const float* Wm, int64_t ldw, int32_t K, int32_t hid
   return gs::launch_check("maxpool_pack_kernel");
 }
 
+
+// bf16 table [n_rows, K] (row pitch in elements) as a 2-D tensor map for tile::gather4: box = one K-block segment
+// (32 columns = 64 bytes) of ONE row - the instruction names four rows -, SWIZZLE_64B to match the UMMA stage layout
+static int32_t make_table_tensor_map(CUtensorMap* out, const void* table, int64_t n_rows, int32_t K, int64_t pitch) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    GS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    GS_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available from this driver");
+    encode = (encode_fn)fn;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)n_rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)pitch * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)gs::MP_KCOLS, 1};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUresult rc = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(table), gdim, gstride, box, estride,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    gs::set_error("cuTensorMapEncodeTiled failed (CUresult %d) for table [%lld, %d] pitch %lld", (int)rc, (long long)n_rows, K,
+                  (long long)pitch);
+    return GS_ERR_CUDA;
+  }
+  return GS_OK;
+}
+
 static int32_t pool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K, int64_t pitch, const int32_t* row_ids,
                               int64_t row0, int64_t n_groups, int32_t k, const void* packed_weights, const float* bias,
                               int32_t hidden, float* out, int64_t ldo, int32_t pool_mean, void* stream) {
   GS_REQUIRE(n_groups >= 0 && k >= 1, "gs_maxpool_mlp_fused: bad n_groups / k");
   if (n_groups == 0) return GS_OK;
   GS_REQUIRE(table_bf16 && packed_weights && out, "gs_maxpool_mlp_fused: NULL pointer");
-  GS_REQUIRE(n_rows > 0 && K >= 1 && pitch >= K, "gs_maxpool_mlp_fused: bad table shape");
+  GS_REQUIRE(n_rows > 0 && n_rows < 0x7fffffffLL && K >= 1 && pitch >= K, "gs_maxpool_mlp_fused: bad table shape");
   GS_REQUIRE((pitch * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(table_bf16) & 15u) == 0,
              "gs_maxpool_mlp_fused: table rows must be 16-byte multiples and 16-byte aligned (pitch %% 8 == 0)");
   GS_REQUIRE((reinterpret_cast<uintptr_t>(packed_weights) & 127u) == 0, "gs_maxpool_mlp_fused: packed weights misaligned");
@@ -377,6 +558,24 @@ static int32_t pool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K,
   int64_t ctas = (int64_t)(gs::sm_count() / prm.n_slices) * prm.n_slices;   // a whole number of slice groups
   if (ctas < prm.n_slices) ctas = prm.n_slices;
   if (ctas > prm.n_tiles * prm.n_slices) ctas = prm.n_tiles * prm.n_slices;
+  if (gs::tuning("k4_producer", 0) == 1) {
+    // TMA gather4 producers (see maxpool_mlp_g4_kernel)
+    static bool g4_attr_set = false;
+    if (!g4_attr_set) {
+      GS_CUDA(cudaFuncSetAttribute(gs::maxpool_mlp_g4_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs::MP_SMEM));
+      GS_CUDA(cudaFuncSetAttribute(gs::maxpool_mlp_g4_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs::MP_SMEM));
+      g4_attr_set = true;
+    }
+    CUtensorMap tmap;
+    const int32_t rc = make_table_tensor_map(&tmap, table_bf16, n_rows, K, pitch);
+    if (rc != GS_OK) return rc;
+    const unsigned threads = (gs::MP_G4_WARPS + 6) * 32;
+    if (prm.kblocks <= gs::MP_RING - 7)
+      gs::maxpool_mlp_g4_kernel<7><<<(unsigned)ctas, threads, gs::MP_SMEM, (cudaStream_t)stream>>>(prm, tmap);
+    else
+      gs::maxpool_mlp_g4_kernel<6><<<(unsigned)ctas, threads, gs::MP_SMEM, (cudaStream_t)stream>>>(prm, tmap);
+    return gs::launch_check("maxpool_mlp_g4_kernel");
+  }
   if (prm.kblocks <= gs::MP_RING - 7)
     gs::maxpool_mlp_kernel<7, 5><<<(unsigned)ctas, gs::MP_THREADS, gs::MP_SMEM, (cudaStream_t)stream>>>(prm);
   else

@@ -286,3 +286,45 @@ def test_toy_ppi_ingest_and_tables():
     f, l = it.next_minibatch_feed_dict()
     assert f["batch_size"] == 512 and l.shape == (512, 121) and set(np.unique(l)) <= {0, 1}
     assert all(it.deg[id_map[u]] > 0 for u in it.train_nodes)
+
+
+@pytest.mark.skipif(not os.path.exists(TOY + "-G.json"), reason="reference example_data not present on this machine")
+def test_config1_toy_ppi_cpu_oracle_path_loss_decreases():
+    """toy-ppi, graphsage_mean, B = 512, max_degree 128, dims [50, 128, 128], 121 sigmoid classes,
+    fanouts [25, 10], lr 0.01 (reference supervised_train.py:32-49) on the CPU oracle path (oracle/torch_ref.py):
+    ingest -> iterator -> sample -> gather -> aggregate -> l2-normalise -> Dense head -> sigmoid xent -> clipped Adam."""
+    import torch
+    from oracle import torch_ref
+    G, feats, id_map, _, class_map = utils.load_data(TOY, normalize=True)
+    np.random.seed(123)
+    it = minibatch.NodeMinibatchIterator(G, id_map, None, class_map, 121, batch_size=512, max_degree=128)
+    n, F, D, C = len(id_map), feats.shape[1], 128, 121
+    feats_t = torch.from_numpy(np.vstack([feats, np.zeros((1, F))]).astype(np.float32))     # zero dummy row (supervised_train.py:133-135)
+    adj_t = torch.from_numpy(it.adj)
+    g = torch.Generator().manual_seed(0)
+
+    def glorot(shape):
+        r = float(np.sqrt(6.0 / (shape[0] + shape[1])))
+        return ((torch.rand(shape, generator=g) * 2 - 1) * r).requires_grad_(True)
+
+    aggs = [{"neigh_weights": glorot((F, D)), "self_weights": glorot((F, D))},
+            {"neigh_weights": glorot((2 * D, D)), "self_weights": glorot((2 * D, D))}]
+    head = {"weights": glorot((2 * D, C)), "bias": torch.zeros(C, requires_grad=True)}
+    params = [v for a in aggs for v in a.values()] + list(head.values())
+    opt = torch.optim.Adam(params, lr=0.01)
+    it.shuffle()
+    losses = []
+    for step in range(12):
+        feed, labels = it.next_minibatch_feed_dict()
+        seeds = torch.tensor(feed["batch"], dtype=torch.int32)
+        out = torch_ref.forward(adj_t, feats_t, seeds, [25, 10], aggs, True, "mean", 123, 2 * step, normalize=True)
+        logits = out @ head["weights"] + head["bias"]
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, torch.from_numpy(labels.astype(np.float32)))
+        opt.zero_grad()
+        loss.backward()
+        for p in params:
+            p.grad.clamp_(-5.0, 5.0)                                  # supervised_models.py:101-103
+        opt.step()
+        losses.append(float(loss))
+    assert np.isfinite(losses).all()
+    assert np.mean(losses[-3:]) < 0.9 * np.mean(losses[:3]), losses
