@@ -124,6 +124,23 @@ def build_aggregators(model):
     return aggs
 
 
+def classification_loss(logits, labels, sigmoid_loss):
+    """reference supervised_models.py:109-117: mean over ALL elements of the sigmoid cross-entropy (multi-label), or the
+    mean over nodes of the softmax cross-entropy."""
+    if sigmoid_loss:
+        return torch.nn.functional.binary_cross_entropy_with_logits(logits, labels, reduction="mean")
+    return (-(labels * torch.log_softmax(logits, dim=1)).sum(dim=1)).mean()
+
+
+def weight_decay_term(params, weight_decay):
+    """weight_decay * tf.nn.l2_loss(var) = weight_decay * sum(var^2) / 2 over every variable (supervised_models.py:103-107)."""
+    total = None
+    for p in params:
+        t = weight_decay * 0.5 * (p * p).sum()
+        total = t if total is None else total + t
+    return total
+
+
 class SupervisedGraphsage(SampleAndAggregate):
     """Supervised GraphSAGE (reference graphsage/supervised_models.py:10-126): the hot path, then
     l2_normalize -> Dense(-> num_classes) -> sigmoid / softmax cross-entropy (+ weight decay), gradients clipped to
@@ -170,15 +187,10 @@ class SupervisedGraphsage(SampleAndAggregate):
         """supervised_models.py:101-118: weight decay * l2_loss(var) over aggregator + head variables, then the
         mean of the per-element sigmoid xent (multi-label) or the mean of the per-node softmax xent."""
         logits = self.logits(batch)
-        labels = labels.to(device=self.device, dtype=torch.float32)
-        loss = logits.new_zeros(())
+        labels = labels.to(device=logits.device, dtype=torch.float32)
+        loss = classification_loss(logits, labels, self.sigmoid_loss)
         if self.weight_decay:
-            for p in self.parameters():
-                loss = loss + self.weight_decay * 0.5 * (p * p).sum()
-        if self.sigmoid_loss:
-            loss = loss + torch.nn.functional.binary_cross_entropy_with_logits(logits, labels, reduction="mean")
-        else:
-            loss = loss + (-(labels * torch.log_softmax(logits, dim=1)).sum(dim=1)).mean()
+            loss = loss + weight_decay_term(self.parameters(), self.weight_decay)
         return loss
 
     def train_step(self, batch, labels):

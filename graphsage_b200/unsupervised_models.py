@@ -11,6 +11,7 @@ import torch
 
 from . import ops
 from .models import SampleAndAggregate
+from .prediction import BipartiteEdgePredLayer, mrr_from_affinities
 from .supervised_models import build_aggregators, differentiable_outputs
 
 
@@ -44,6 +45,10 @@ class UnsupervisedGraphsage(SampleAndAggregate):
         self.learning_rate, self.weight_decay = learning_rate, weight_decay
         self.neg_sampler = UnigramNegativeSampler(degrees, 0.75, seed, device)      # models.py:336-343
         self.aggregators = build_aggregators(self)
+        dim_mult = 2 if self.concat else 1
+        self.link_pred_layer = BipartiteEdgePredLayer(dim_mult * self.dims[-1], dim_mult * self.dims[-1], placeholders,
+                                                      neg_sample_weights=self.neg_sample_weights, bilinear_weights=False,
+                                                      device=device, name="edge_predict")      # models.py:362-365
         for p in self.parameters():
             p.requires_grad_(True)
         self.optimizer = torch.optim.Adam(self.parameters(), lr=self.learning_rate)
@@ -64,24 +69,17 @@ class UnsupervisedGraphsage(SampleAndAggregate):
         """weight decay + BipartiteEdgePredLayer._xent_loss (prediction.py:102-110), divided by the batch size
         (models.py:378)."""
         o1, o2, on, _ = self._passes(batch1, batch2)
-        aff = (o1 * o2).sum(dim=1)                                                   # prediction.py:78
-        neg_aff = o1 @ on.t()                                                        # prediction.py:91
-        loss = torch.nn.functional.softplus(-aff).sum() + \
-            self.neg_sample_weights * torch.nn.functional.softplus(neg_aff).sum()
+        loss = self.link_pred_layer.loss(o1, o2, on)
         if self.weight_decay:
             for p in self.parameters():
                 loss = loss + self.weight_decay * 0.5 * (p * p).sum()
-        self._last = (aff.detach(), neg_aff.detach())
+        with torch.no_grad():
+            self._last = (self.link_pred_layer.affinity(o1, o2), self.link_pred_layer.neg_cost(o1, on))
         return loss / float(o1.shape[0])
 
     def mrr(self):
-        """models.py:393-405 on the affinities of the last loss() call: rank of the true pair among
-        [negatives..., true] by descending affinity."""
-        aff, neg_aff = self._last
-        aff_all = torch.cat([neg_aff, aff.unsqueeze(1)], dim=1)
-        order = torch.argsort(aff_all, dim=1, descending=True, stable=True)
-        ranks = torch.argsort(order, dim=1, stable=True)
-        return (1.0 / (ranks[:, -1] + 1).float()).mean()
+        """models.py:393-405 on the affinities of the last loss() call."""
+        return mrr_from_affinities(*self._last)
 
     def train_step(self, batch1, batch2):
         self.optimizer.zero_grad(set_to_none=True)

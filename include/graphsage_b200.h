@@ -52,7 +52,13 @@ typedef enum {
 
 int32_t gs_version(void);
 const char* gs_last_error_string(void);
-/* tuning knobs for experiments (e.g. "gather_variant" 0=ldg 1=tma-bulk); returns previous value */
+/* Tuning knobs for experiments; returns the previous value.  Keys (default):
+ *   gather_variant (2)      gs_gather_mean / gs_gather_rows: 2 grouped double-buffered TMA, 1 whole-node TMA, 0 LDG
+ *   gather_ctas_per_sm (8)  grid cap of the LDG / simple gather kernels
+ *   gemm_async (0)          gs_sage_gemm tcgen05 producers: 1 = cp.async staging instead of register prefetch
+ *   mma_issue (1)           tcgen05 issue form: 1 = whole warp + elect.sync (tensor-pipe floor), 0 = single thread
+ *   k4_producer (0)         gs_maxpool/meanpool_mlp_fused gather-A producers: 0 = cp.async, 1 = TMA tile::gather4
+ * The Python host also reads them from the environment: GS_TUNING="key=value,key=value". */
 int32_t gs_set_tuning(const char* key, int32_t value);
 
 /* ---------------------------------------------------------------------------------------------

@@ -9,6 +9,7 @@ Nothing from /root/reference is copied: the modules are imported from where they
 """
 import os
 import sys
+import types
 
 import numpy as np
 
@@ -294,16 +295,77 @@ def golden_iterators():
     save("iterators", **out)
 
 
+def golden_heads():
+    """Loss heads either side of the hot path's output: BipartiteEdgePredLayer (reference prediction.py:68-122),
+    the MRR of SampleAndAggregate._accuracy (models.py:393-405) and SupervisedGraphsage._loss / predict
+    (supervised_models.py:101-126), executed from the reference's own files."""
+    from graphsage.prediction import BipartiteEdgePredLayer
+    from graphsage.supervised_models import SupervisedGraphsage
+    r = np.random.RandomState(11)
+    B, NEG, D, C = 13, 20, 16, 6
+
+    def unit(x):
+        return (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)
+
+    o1, o2, on = unit(r.randn(B, D)), unit(r.randn(B, D)), unit(r.randn(NEG, D))
+    o2[3] = o1[3]                                   # a pair that ranks first
+    on[5] = o1[7]                                   # a negative that beats a true pair
+    out = {"o1": o1, "o2": o2, "on": on}
+    ph = {"dropout": 0.0}
+    for fn in ("xent", "skipgram", "hinge"):
+        layer = BipartiteEdgePredLayer(D, D, ph, act=tf.nn.sigmoid, loss_fn=fn, bilinear_weights=False, name="edge_predict")
+        out["loss_" + fn] = np.float64(layer.loss(o1, o2, on))
+    out["aff"] = layer.affinity(o1, o2)
+    out["neg_aff"] = layer.neg_cost(o1, on)
+    layer = BipartiteEdgePredLayer(D, D, ph, loss_fn="xent", neg_sample_weights=0.25, bilinear_weights=True, name="bil")
+    out["bil_w"] = layer.vars["weights"]
+    out["bil_aff"], out["bil_neg_aff"] = layer.affinity(o1, o2), layer.neg_cost(o1, on)
+    out["bil_loss"] = np.float64(layer.loss(o1, o2, on))
+    # ---- MRR
+    stub = _Stub()
+    stub.link_pred_layer = BipartiteEdgePredLayer(D, D, ph, bilinear_weights=False, name="edge_predict2")
+    stub.outputs1, stub.outputs2, stub.neg_outputs, stub.batch_size = o1, o2, on, B
+    tf.app.flags.FLAGS.neg_sample_size = NEG
+    SampleAndAggregate._accuracy(stub)
+    out["mrr"], out["ranks"] = np.float64(stub.mrr), stub.ranks
+    # ---- supervised loss / predictions
+    logits = r.randn(B, C).astype(np.float32) * 2
+    multi = (r.rand(B, C) < 0.3).astype(np.float32)
+    onehot = np.eye(C, dtype=np.float32)[r.randint(0, C, size=B)]
+    agg_vars = [{"neigh_weights": r.randn(5, 4).astype(np.float32), "self_weights": r.randn(5, 4).astype(np.float32)},
+                {"weights": r.randn(4, 3).astype(np.float32)}]
+    head_vars = {"weights": r.randn(8, C).astype(np.float32), "bias": r.randn(C).astype(np.float32)}
+    out.update(logits=logits, multi=multi, onehot=onehot, head_w=head_vars["weights"], head_b=head_vars["bias"],
+               a0_nw=agg_vars[0]["neigh_weights"], a0_sw=agg_vars[0]["self_weights"], a1_w=agg_vars[1]["weights"])
+    for sig, labels, tag in ((True, multi, "sig"), (False, onehot, "soft")):
+        for wd in (0.0, 0.05):
+            st = _Stub()
+            st.aggregators = [types.SimpleNamespace(vars=v) for v in agg_vars]
+            st.node_pred = types.SimpleNamespace(vars=head_vars)
+            st.node_preds, st.sigmoid_loss, st.placeholders, st.loss = logits, sig, {"labels": labels}, 0
+            tf.app.flags.FLAGS.weight_decay = wd
+            SupervisedGraphsage._loss(st)
+            out["sup_%s_wd%d" % (tag, int(wd > 0))] = np.float64(st.loss)
+        out["pred_" + tag] = SupervisedGraphsage.predict(st)
+    tf.app.flags.FLAGS.weight_decay = 0.0
+    save("heads", **out)
+
+
+def _standalone(fn):
+    """meanpool / iterators / heads were added after the first four fixtures: each starts from a fresh initialiser
+    stream, so regenerating everything reproduces every committed file."""
+    tf_shim.INIT_RNG.seed(2024)
+    fn()
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "meanpool":
-        golden_meanpool()
-        sys.exit(0)
-    if len(sys.argv) > 1 and sys.argv[1] == "iterators":
-        golden_iterators()
+    later = {"meanpool": golden_meanpool, "iterators": golden_iterators, "heads": golden_heads}
+    if len(sys.argv) > 1:
+        _standalone(later[sys.argv[1]])
         sys.exit(0)
     golden_sampler()
     golden_aggregators()
     golden_khop()
     golden_adjacency()
-    golden_meanpool()
-    golden_iterators()
+    for fn in later.values():
+        _standalone(fn)

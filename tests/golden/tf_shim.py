@@ -85,7 +85,7 @@ def install():
     tf.transpose = lambda x, perm=None: np.transpose(_arr(x), perm)
     tf.reshape = lambda x, shape: np.reshape(_arr(x), tuple(int(s) for s in shape))
     tf.shape = lambda x: _arr(x).shape
-    tf.concat = lambda vals, axis: np.concatenate([_arr(v) for v in vals], axis=axis)
+    tf.concat = lambda values=None, axis=None, **k: np.concatenate([_arr(v) for v in values], axis=axis)
     tf.expand_dims = lambda x, axis: np.expand_dims(_arr(x), axis)
     tf.cast = lambda x, dtype: _arr(x).astype(dtype)
 
@@ -123,11 +123,43 @@ def install():
 
     tf.nn = types.SimpleNamespace(
         embedding_lookup=lambda params, ids: _arr(params)[_arr(ids).astype(np.int64)],
-        relu=lambda x: np.maximum(_arr(x), 0),
+        relu=lambda x, name=None: np.maximum(_arr(x), 0),
         dropout=dropout,
         l2_normalize=l2_normalize,
         sigmoid=lambda x: 1.0 / (1.0 + np.exp(-_arr(x))),
         tanh=lambda x: np.tanh(_arr(x)),
     )
+    # ---- loss-head ops (reference prediction.py, models.py:384-405, supervised_models.py:101-126); formulas as
+    # documented for TensorFlow: sigmoid xent = max(x, 0) - x z + log(1 + exp(-|x|)); softmax xent = -sum z log_softmax(x);
+    # l2_loss = sum(t^2) / 2; top_k sorts descending and breaks ties by the lower index first
+    def sigmoid_xent(labels=None, logits=None, **k):
+        x, z = _arr(logits), _arr(labels)
+        return np.maximum(x, 0) - x * z + np.log1p(np.exp(-np.abs(x)))
+
+    def _log_softmax(x):
+        x = _arr(x)
+        m = x.max(axis=-1, keepdims=True)
+        return x - m - np.log(np.exp(x - m).sum(axis=-1, keepdims=True))
+
+    def softmax_xent(labels=None, logits=None, **k):
+        return -(_arr(labels) * _log_softmax(logits)).sum(axis=-1)
+
+    def top_k(x, k=1, **kw):
+        x = _arr(x)
+        idx = np.argsort(-x, axis=-1, kind="stable")[..., :int(k)]
+        return np.take_along_axis(x, idx, axis=-1), idx.astype(np.int32)
+
+    tf.nn.sigmoid_cross_entropy_with_logits = sigmoid_xent
+    tf.nn.softmax_cross_entropy_with_logits = softmax_xent
+    tf.nn.softmax = lambda x: np.exp(_log_softmax(x))
+    tf.nn.l2_loss = lambda t: (_arr(t) * _arr(t)).sum(dtype=_arr(t).dtype) / 2
+    tf.nn.top_k = top_k
+    tf.ones_like = lambda x: np.ones_like(_arr(x))
+    tf.zeros_like = lambda x: np.zeros_like(_arr(x))
+    tf.div = lambda a, b: _arr(a) / _arr(b)
+    tf.log = lambda x: np.log(_arr(x))
+    tf.exp = lambda x: np.exp(_arr(x))
+    tf.subtract = lambda a, b, name=None: _arr(a) - _arr(b)
+
     sys.modules["tensorflow"] = tf
     return tf
