@@ -2,6 +2,8 @@
 #include <stdarg.h>
 
 #include <map>
+#include <set>
+#include <utility>
 #include <mutex>
 #include <string>
 
@@ -36,13 +38,28 @@ int32_t tuning(const char* key, int32_t dflt) {
 }
 
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  static int n[64] = {0};                        // per device ordinal
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev] = v;
   }
-  return n;
+  return n[dev];
+}
+
+int32_t ensure_dyn_smem(const void* kernel, int bytes) {
+  // the attribute belongs to the kernel in the CURRENT device's context, so remember it per (device, kernel)
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> done;
+  int dev = 0;
+  GS_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> l(mu);
+  if (done.count(std::make_pair(dev, kernel))) return GS_OK;
+  GS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.insert(std::make_pair(dev, kernel));
+  return GS_OK;
 }
 
 }  // namespace gs

@@ -13,6 +13,8 @@ namespace gs {
 void set_error(const char* fmt, ...);
 int32_t cuda_fail(cudaError_t e, const char* what);
 int32_t tuning(const char* key, int32_t dflt);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (current device, kernel); GS_OK or GS_ERR_CUDA
+int32_t ensure_dyn_smem(const void* kernel, int bytes);
 
 #define GS_REQUIRE(cond, ...)            \
   do {                                   \

@@ -486,10 +486,9 @@ int32_t gs_gather_rows(const void* feats, int32_t dtype, int64_t n_rows, int32_t
                       row_bytes <= pitch * es && row_bytes <= out_pitch * es && row_bytes * 32 <= 200 * 1024;
   if (tma_ok && gs::tuning("gather_variant", 2) != 0) {
     size_t smem = (size_t)row_bytes * 32;
-    static bool attr_set = false;
-    if (!attr_set) {
-      GS_CUDA(cudaFuncSetAttribute(gs::gather_rows_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set = true;
+    {
+      const int32_t rc_attr = gs::ensure_dyn_smem((const void*)gs::gather_rows_tma_kernel, 200 * 1024);
+      if (rc_attr != GS_OK) return rc_attr;
     }
     int per_sm = (int)((220 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
@@ -551,10 +550,9 @@ int32_t gs_gather_mean(const void* src, int32_t dtype, int64_t n_src_rows, int32
   const size_t smem = (size_t)row_bytes * (kmax + 1);
   const int variant = gs::tuning("gather_variant", 2);   // 2: grouped double-buffered TMA (default), 1: whole-node TMA, 0: LDG
   if (variant == 2 && ncol4 <= 2 * 160) {
-    static bool attr2_set = false;
-    if (!attr2_set) {
-      GS_CUDA(cudaFuncSetAttribute(gs::gather_mean_tma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr2_set = true;
+    {
+      const int32_t rc_attr = gs::ensure_dyn_smem((const void*)gs::gather_mean_tma2_kernel, 200 * 1024);
+      if (rc_attr != GS_OK) return rc_attr;
     }
     const size_t smem2 = (size_t)2 * gs::kGroupRows * row_bytes;
     int threads = ((ncol4 + 31) / 32) * 32;
@@ -573,10 +571,9 @@ int32_t gs_gather_mean(const void* src, int32_t dtype, int64_t n_src_rows, int32
     return gs::launch_check("gather_mean_tma2_kernel");
   }
   if (variant >= 1 && smem <= 200 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      GS_CUDA(cudaFuncSetAttribute(gs::gather_mean_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set = true;
+    {
+      const int32_t rc_attr = gs::ensure_dyn_smem((const void*)gs::gather_mean_tma_kernel, 200 * 1024);
+      if (rc_attr != GS_OK) return rc_attr;
     }
     int threads = ((ncol4 + 31) / 32) * 32;
     if (threads > 192) threads = 192;

@@ -486,11 +486,9 @@ static int32_t launch_pack(const TcParams& prm, unsigned char* ws, cudaStream_t 
 template <int MODE, bool ASYNC>
 static int32_t launch_tc_impl(const TcParams& prm, const unsigned char* ws, cudaStream_t st) {
   using C = TcCfg<MODE, ASYNC>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GS_CUDA(cudaFuncSetAttribute(sage_gemm_tc_kernel<MODE, ASYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 C::SMEM_BYTES));
-    attr_set = true;
+  {
+    const int32_t rc_attr = ensure_dyn_smem((const void*)sage_gemm_tc_kernel<MODE, ASYNC>, C::SMEM_BYTES);
+    if (rc_attr != GS_OK) return rc_attr;
   }
   int tiles_n = prm.p[0].ntiles;
   if (prm.combine == GS_COMBINE_CONCAT && prm.n_parts == 2) tiles_n += prm.p[1].ntiles;

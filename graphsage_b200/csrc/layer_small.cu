@@ -300,10 +300,9 @@ extern "C" int32_t gs_sage_layer_small(const float* src, int64_t n_src_rows, int
                           : (ncolp <= gs::LS_THREADS ? gs::LS_THREADS / ncolp : 1);
   const size_t smem = (size_t)(2 * gs::LS_ROWS * F + nslices * gs::LS_ROWS * ncolp + gs::LS_ROWS * 16) * sizeof(float);
   GS_REQUIRE(smem <= 200 * 1024, "gs_sage_layer_small: needs %zu bytes of shared memory", smem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    GS_CUDA(cudaFuncSetAttribute(gs::sage_layer_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+  {
+    const int32_t rc_attr = gs::ensure_dyn_smem((const void*)gs::sage_layer_small_kernel, 200 * 1024);
+    if (rc_attr != GS_OK) return rc_attr;
   }
   unsigned blocks = (unsigned)((segment_host->n + gs::LS_ROWS - 1) / gs::LS_ROWS);
   gs::sage_layer_small_kernel<<<blocks, gs::LS_THREADS, smem, (cudaStream_t)stream>>>(prm);

@@ -549,22 +549,20 @@ static int32_t pool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K,
   prm.wimg = (const unsigned char*)packed_weights; prm.bias = bias; prm.out = out; prm.ldo = ldo;
   prm.pool_mean = pool_mean;
   prm.issue_elect = gs::tuning("mma_issue", 1) != 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GS_CUDA(cudaFuncSetAttribute(gs::maxpool_mlp_kernel<7, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs::MP_SMEM));
-    GS_CUDA(cudaFuncSetAttribute(gs::maxpool_mlp_kernel<6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs::MP_SMEM));
-    attr_set = true;
+  {
+    int32_t rc_attr = gs::ensure_dyn_smem((const void*)gs::maxpool_mlp_kernel<7, 5>, gs::MP_SMEM);
+    if (rc_attr == GS_OK) rc_attr = gs::ensure_dyn_smem((const void*)gs::maxpool_mlp_kernel<6, 4>, gs::MP_SMEM);
+    if (rc_attr != GS_OK) return rc_attr;
   }
   int64_t ctas = (int64_t)(gs::sm_count() / prm.n_slices) * prm.n_slices;   // a whole number of slice groups
   if (ctas < prm.n_slices) ctas = prm.n_slices;
   if (ctas > prm.n_tiles * prm.n_slices) ctas = prm.n_tiles * prm.n_slices;
   if (gs::tuning("k4_producer", 0) == 1) {
     // TMA gather4 producers (see maxpool_mlp_g4_kernel)
-    static bool g4_attr_set = false;
-    if (!g4_attr_set) {
-      GS_CUDA(cudaFuncSetAttribute(gs::maxpool_mlp_g4_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs::MP_SMEM));
-      GS_CUDA(cudaFuncSetAttribute(gs::maxpool_mlp_g4_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs::MP_SMEM));
-      g4_attr_set = true;
+    {
+      int32_t rc_attr = gs::ensure_dyn_smem((const void*)gs::maxpool_mlp_g4_kernel<7>, gs::MP_SMEM);
+      if (rc_attr == GS_OK) rc_attr = gs::ensure_dyn_smem((const void*)gs::maxpool_mlp_g4_kernel<6>, gs::MP_SMEM);
+      if (rc_attr != GS_OK) return rc_attr;
     }
     CUtensorMap tmap;
     const int32_t rc = make_table_tensor_map(&tmap, table_bf16, n_rows, K, pitch);
