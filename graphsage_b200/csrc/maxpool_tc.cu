@@ -100,7 +100,7 @@ __device__ __forceinline__ void mp_stamp(uint32_t tcount, int slot) {
 
 // MMA issuer warp: waits for each A stage, issues the two K = 16 MMAs of the K-block against the resident weights,
 // commits the stage back to the producers and, after a tile's last K-block, the accumulator to the epilogue.
-template <int MP_SA>
+template <int MP_SA, int CL = 1>
 __device__ __forceinline__ void mp_mma_role(const MpParams& prm, int lane, int kblocks, int64_t tile0, int64_t tile_step,
                                             uint32_t tmem_base, uint64_t* full_a, uint64_t* empty_a, uint64_t* acc_full,
                                             uint64_t* acc_empty, uint64_t& b_full, unsigned char* a_ring,
@@ -128,7 +128,10 @@ __device__ __forceinline__ void mp_mma_role(const MpParams& prm, int lane, int k
         for (int k2 = 0; k2 < 2; ++k2)            // two K = 16 steps per 32-column K-block (32 B apart inside the atom)
           umma_ss_elect<true>(tmem_acc, adesc + (uint64_t)(k2 * 2), bdesc + (uint64_t)(k2 * 2), idesc,
                               (kb > 0 || k2 > 0) ? 1u : 0u);
-        umma_commit_elect(&empty_a[s]);
+        if constexpr (CL > 1)                       // frees the stage in every CTA of the cluster
+          umma_commit_elect_multicast(&empty_a[s], (uint16_t)((1u << CL) - 1u));
+        else
+          umma_commit_elect(&empty_a[s]);
         if (kb == kblocks - 1) umma_commit_elect(&acc_full[buf]);
         if (lane == 0 && kb == kblocks - 1) mp_stamp(tcount, 4);
       } else if (lane == 0) {
@@ -466,6 +469,143 @@ __global__ void __launch_bounds__((MP_G4_WARPS + 6) * 32, 1)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Variant 2 (GS_TUNING=k4_producer=2; compiled, not yet run on a GPU): as the gather4 variant, plus thread-block clusters.
+// The n_slices CTAs that work on the SAME M tile (one per 128-wide slice of the hidden dimension) form a cluster of
+// CL = n_slices (2 or 4) CTAs; each gathers only 128 / CL of the tile's rows and MULTICASTS them into the A stage of
+// every CTA of the cluster, so an A row crosses the L2 -> SM fabric once per cluster instead of once per slice
+// (that fabric's chip-wide cap, not the tensor pipe, bounds the non-multicast kernels once the proxy fence is gone).
+// Hand-off: a CTA's full barrier collects its own expect_tx arrive + 8 KB of transactions from all CL issuers; its
+// empty barrier has CL arrivals - every CTA's MMA warp commits with .multicast::cluster to all CL empty barriers -,
+// so a producer re-fills a stage only when every CTA of the cluster has consumed it.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_gather4_multicast(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, uint16_t mask,
+                                                      int col, int r0, int r1, int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5, %6, %7, %8}], [%2], %3;" ::"r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "h"(mask), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
+
+template <int MP_SA, int CL>
+__global__ void __launch_bounds__((MP_G4_WARPS + 6) * 32, 1)
+    maxpool_mlp_g4mc_kernel(const __grid_constant__ MpParams prm, const __grid_constant__ CUtensorMap tmap) {
+  static_assert(CL == 2 || CL == 4, "cluster = the 2 or 4 hidden slices of one M tile");
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_a[MP_SA], empty_a[MP_SA], acc_full[2], acc_empty[2], b_full;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float bias_s[128];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* b_res = smem;                                        // resident weight slice
+  unsigned char* a_ring = smem + (MP_RING - MP_SA) * MP_IMG;
+  float* stage = reinterpret_cast<float*>(smem + MP_RING * MP_IMG);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x % prm.n_slices;                        // == rank in the cluster (n_slices == CL)
+  const int64_t tile0 = blockIdx.x / prm.n_slices, tile_step = gridDim.x / prm.n_slices;
+  const int kblocks = prm.kblocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MP_SA; ++s) {
+      mbar_init(&full_a[s], 1);           // own expect_tx arrive; the 8 KB arrive from all CL issuers
+      mbar_init(&empty_a[s], CL);         // one multicast commit per CTA of the cluster
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);        // one arrive per epilogue warp
+    }
+    mbar_init(&b_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == MP_G4_WARPS) {
+    tmem_alloc(&tmem_base_smem, 256);     // two 128-column fp32 accumulators
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                     // every CTA's barriers exist before any remote arrive / multicast write
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp < MP_G4_WARPS) {
+    // =============================== gather-A producers (TMA gather4, multicast) ===============================
+    constexpr int ROWS_PER_CTA = 128 / CL;          // this CTA's share of the tile's rows
+    constexpr int LANES = ROWS_PER_CTA / 4;         // one gather4 (4 rows) per active lane
+    const int rank = (int)cluster_ctarank();
+    const int rows_valid = prm.G * prm.k;
+    const int64_t total_rows = prm.n_groups * prm.k;
+    const int64_t my_tiles = tile0 < prm.n_tiles ? (prm.n_tiles - tile0 + tile_step - 1) / tile_step : 0;
+    const int64_t total_it = my_tiles * kblocks;
+    const int oob_row = (int)prm.n_rows;            // out of bounds for the tensor map: the TMA writes zeros
+    const int row_base = rank * ROWS_PER_CTA + 4 * lane;
+    int cur[4], nxt[4];
+    auto load_ids = [&](int64_t tl, int (&ids)[4]) {
+      const int64_t t = tile0 + tl * tile_step;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = row_base + i;
+        const int64_t flat = t * rows_valid + r;
+        int64_t id = oob_row;
+        if (lane < LANES && tl < my_tiles && r < rows_valid && flat < total_rows) {
+          id = prm.row_ids ? (int64_t)prm.row_ids[flat] : prm.row0 + flat;
+          if (id < 0 || id >= prm.n_rows) id = prm.n_rows - 1;
+        }
+        ids[i] = (int)id;
+      }
+    };
+    int64_t tl = 0;
+    int kb = warp;
+    while (kb >= kblocks) { kb -= kblocks; ++tl; }
+    load_ids(tl, cur);
+    load_ids(tl + 1, nxt);
+    for (int64_t it = warp; it < total_it; it += MP_G4_WARPS) {
+      const int s = (int)(it % MP_SA);
+      mbar_wait(&empty_a[s], ((uint32_t)(it / MP_SA) & 1u) ^ 1u);      // every CTA of the cluster has consumed the stage
+      if (lane == 0) mbar_expect_tx(&full_a[s], (uint32_t)MP_IMG);
+      __syncwarp();
+      if (lane < LANES)
+        tma_gather4_multicast(a_ring + (size_t)s * MP_IMG + (size_t)(row_base / 4) * 256, &tmap, &full_a[s],
+                              (uint16_t)((1u << CL) - 1u), kb * MP_KCOLS, cur[0], cur[1], cur[2], cur[3]);
+      kb += MP_G4_WARPS;
+      int adv = 0;
+      while (kb >= kblocks) { kb -= kblocks; ++adv; }
+      if (adv == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+        tl += 1;
+        load_ids(tl + 1, nxt);
+      } else if (adv > 1) {
+        tl += adv;
+        load_ids(tl, cur);
+        load_ids(tl + 1, nxt);
+      }
+    }
+  } else if (warp == MP_G4_WARPS) {
+    mp_mma_role<MP_SA, CL>(prm, lane, kblocks, tile0, tile_step, tmem_base, full_a, empty_a, acc_full, acc_empty, b_full,
+                           a_ring, b_res);
+  } else if (warp == MP_G4_WARPS + 1) {
+    mp_weights_role(prm, lane, slice, kblocks, b_full, b_res);
+  } else {
+    mp_epilogue_role(prm, (int)threadIdx.x - (MP_G4_WARPS + 2) * 32, warp, lane, slice, tile0, tile_step, tmem_base, acc_full,
+                     acc_empty, stage, bias_s);
+  }
+  __syncthreads();
+  cluster_sync_all();                     // no CTA leaves while a peer may still write its stages or signal its barriers
+  if (warp == MP_G4_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 }  // namespace gs
 
 extern "C" {
@@ -557,7 +697,37 @@ static int32_t pool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K,
   int64_t ctas = (int64_t)(gs::sm_count() / prm.n_slices) * prm.n_slices;   // a whole number of slice groups
   if (ctas < prm.n_slices) ctas = prm.n_slices;
   if (ctas > prm.n_tiles * prm.n_slices) ctas = prm.n_tiles * prm.n_slices;
-  if (gs::tuning("k4_producer", 0) == 1) {
+  const int producer = gs::tuning("k4_producer", 0);
+  if (producer == 2 && (prm.n_slices == 2 || prm.n_slices == 4) && prm.issue_elect) {
+    // clusters of n_slices CTAs, TMA gather4 multicast (see maxpool_mlp_g4mc_kernel)
+    CUtensorMap tmap;
+    const int32_t rc = make_table_tensor_map(&tmap, table_bf16, n_rows, K, pitch);
+    if (rc != GS_OK) return rc;
+    const bool sa7 = prm.kblocks <= gs::MP_RING - 7;
+    const void* fn = prm.n_slices == 4
+                         ? (sa7 ? (const void*)gs::maxpool_mlp_g4mc_kernel<7, 4> : (const void*)gs::maxpool_mlp_g4mc_kernel<6, 4>)
+                         : (sa7 ? (const void*)gs::maxpool_mlp_g4mc_kernel<7, 2> : (const void*)gs::maxpool_mlp_g4mc_kernel<6, 2>);
+    const int32_t rc_attr = gs::ensure_dyn_smem(fn, gs::MP_SMEM);
+    if (rc_attr != GS_OK) return rc_attr;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)ctas);                      // a multiple of n_slices: whole clusters
+    cfg.blockDim = dim3((gs::MP_G4_WARPS + 6) * 32);
+    cfg.dynamicSmemBytes = gs::MP_SMEM;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = (unsigned)prm.n_slices;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    void* args[2] = {(void*)&prm, (void*)&tmap};
+    GS_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+    return gs::launch_check("maxpool_mlp_g4mc_kernel");
+  }
+  if (producer >= 1) {
+
     // TMA gather4 producers (see maxpool_mlp_g4_kernel)
     {
       int32_t rc_attr = gs::ensure_dyn_smem((const void*)gs::maxpool_mlp_g4_kernel<7>, gs::MP_SMEM);

@@ -79,6 +79,16 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
       : "memory");
 }
 
+// as umma_commit_elect, arriving on the barrier at the same shared-memory offset in every CTA of `cta_mask` (cluster)
+__device__ __forceinline__ void umma_commit_elect_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane base + t)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

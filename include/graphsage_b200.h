@@ -57,7 +57,8 @@ const char* gs_last_error_string(void);
  *   gather_ctas_per_sm (8)  grid cap of the LDG / simple gather kernels
  *   gemm_async (0)          gs_sage_gemm tcgen05 producers: 1 = cp.async staging instead of register prefetch
  *   mma_issue (1)           tcgen05 issue form: 1 = whole warp + elect.sync (tensor-pipe floor), 0 = single thread
- *   k4_producer (0)         gs_maxpool/meanpool_mlp_fused gather-A producers: 0 = cp.async, 1 = TMA tile::gather4
+ *   k4_producer (0)         gs_maxpool/meanpool_mlp_fused gather-A producers: 0 = cp.async, 1 = TMA tile::gather4,
+ *                           2 = gather4 multicast over clusters of the hidden slices (both compiled, not yet measured)
  * The Python host also reads them from the environment: GS_TUNING="key=value,key=value". */
 int32_t gs_set_tuning(const char* key, int32_t value);
 

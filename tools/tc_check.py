@@ -57,7 +57,8 @@ for flag in (1, 0):
 lib.gs_set_tuning(b"mma_issue", 1)
 
 if os.environ.get("TC_CHECK_G4", "0") == "1":
-    # experimental K4 producer (TMA gather4): same inputs, both producers, outputs must be identical bit for bit
+    # experimental K4 producers (1: TMA gather4, 2: + cluster multicast; hidden 128 has one slice, so 2 falls back to 1):
+    # same inputs, all producers, outputs must be identical bit for bit
     # (same MMAs in the same order on the same operand bits)
     for nb, kk, KK, HH in ((3, 25, 602, 512), (77, 10, 602, 512), (5, 25, 50, 128), (512 * 10, 25, 602, 512)):
         tb = torch.randn((4096 if nb < 1000 else n_rows, ops.pad_cols(KK)), device=dev).to(torch.bfloat16)
@@ -65,13 +66,13 @@ if os.environ.get("TC_CHECK_G4", "0") == "1":
         W = torch.randn(KK, HH, device=dev) / 25.0
         b = torch.randn(HH, device=dev) * 0.1
         outs = []
-        for flag in (0, 1):
+        for flag in (0, 1, 2):
             lib.gs_set_tuning(b"k4_producer", flag)
             outs.append(ops.maxpool_mlp_fused(tb[:, :KK], nb, kk, W, b, ops.PackedMlpWeights(), row_ids=rid).clone())
             torch.cuda.synchronize()
-        print("k4_producer 1 vs 0  groups=%d k=%d K=%d hidden=%d: max |diff| = %.3g" % (
-            nb, kk, KK, HH, float((outs[0] - outs[1]).abs().max())), flush=True)
-    for flag in (0, 1):
+        print("k4_producer 1 / 2 vs 0  groups=%d k=%d K=%d hidden=%d: max |diff| = %.3g / %.3g" % (
+            nb, kk, KK, HH, float((outs[0] - outs[1]).abs().max()), float((outs[0] - outs[2]).abs().max())), flush=True)
+    for flag in (0, 1, 2):
         lib.gs_set_tuning(b"k4_producer", flag)
         t = timeit(lambda: ops.maxpool_mlp_fused(table[:, :F], B * 10, 25, Wm, bm, pk, row_ids=ids), n=20)
         print("k4_producer=%d  K4 maxpool hop2: %.1f us  %.1f TFLOP/s" % (flag, t, 2.0 * B * 250 * F * H / t / 1e6), flush=True)
