@@ -326,3 +326,48 @@ def test_config1_toy_ppi_cpu_oracle_path_loss_decreases():
         losses.append(float(loss.detach()))
     assert np.isfinite(losses).all()
     assert np.mean(losses[-3:]) < 0.9 * np.mean(losses[:3]), losses
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_graphs_tables_are_consistent_with_the_graph(seed):
+    """Randomised cross-check of graph.py -> to_csr -> construct_adj against a plain set-of-edges model."""
+    r = np.random.RandomState(seed)
+    n, md = int(r.randint(5, 60)), int(r.randint(1, 9))
+    names = ["v%d" % i for i in r.permutation(n)]
+    G = Graph()
+    edges = set()
+    for u in names:
+        G.add_node(u, val=bool(r.rand() < 0.2), test=bool(r.rand() < 0.2))
+    for _ in range(int(r.randint(0, 4 * n))):
+        a, b = names[r.randint(n)], names[r.randint(n)]
+        G.add_edge(a, b)
+        edges.add(frozenset((a, b)))
+    assert {frozenset(e) for e in G.edges()} == edges and len(G.edges()) == len(edges)
+    for u, v in G.edges():
+        G[u][v]["train_removed"] = bool(G.node[u]["val"] or G.node[u]["test"] or G.node[v]["val"] or G.node[v]["test"])
+    id2idx = {u: i for i, u in enumerate(sorted(names))}
+    it = minibatch.NodeMinibatchIterator(G, id2idx, None, {u: 0 for u in names}, 2, batch_size=3, max_degree=md,
+                                         rng=np.random.RandomState(seed))
+    idx2id = {i: u for u, i in id2idx.items()}
+    for u in names:
+        iu = id2idx[u]
+        vt = G.node[u]["val"] or G.node[u]["test"]
+        train_nb = {id2idx[v] for v in G.neighbors(u) if not G[u][v]["train_removed"]}
+        all_nb = {id2idx[v] for v in G.neighbors(u)}
+        if vt or not train_nb:
+            assert (it.adj[iu] == n).all()
+            assert it.deg[iu] == (0 if vt else len(train_nb))
+        else:
+            assert set(it.adj[iu]) <= train_nb and it.deg[iu] == len(train_nb)
+            if len(train_nb) >= md:
+                assert len(set(it.adj[iu])) == md                    # subsampled without replacement
+            else:
+                assert set(it.adj[iu]) <= train_nb and len(it.adj[iu]) == md
+        if all_nb:
+            assert set(it.test_adj[iu]) <= all_nb
+            assert len(set(it.test_adj[iu])) == min(md, len(all_nb)) or len(all_nb) < md
+        else:
+            assert (it.test_adj[iu] == n).all()
+    assert (it.adj[n] == n).all() and (it.test_adj[n] == n).all()
+    assert set(it.train_nodes) == {u for u in names if not (G.node[u]["val"] or G.node[u]["test"]) and it.deg[id2idx[u]] > 0}
+    assert idx2id[0] == sorted(names)[0]
