@@ -36,18 +36,19 @@ class Layer(object):
     """reference graphsage/layers.py:28-70: kwarg whitelist, auto name `<class>_<uid>`, .vars dict,
     __call__ -> _call."""
 
+    ALLOWED_KWARGS = frozenset(("name", "logging", "model_size"))
+
     def __init__(self, **kwargs):
-        allowed_kwargs = {"name", "logging", "model_size"}
-        for kwarg in kwargs.keys():
-            assert kwarg in allowed_kwargs, "Invalid keyword argument: " + kwarg
-        name = kwargs.get("name")
-        if not name:
-            layer = self.__class__.__name__.lower()
-            name = layer + "_" + str(get_layer_uid(layer))
-        self.name = name
-        self.vars = {}
-        self.logging = kwargs.get("logging", False)
-        self.sparse_inputs = False
+        unknown = [k for k in kwargs if k not in self.ALLOWED_KWARGS]
+        assert not unknown, "Invalid keyword argument: " + unknown[0]
+        self.vars, self.sparse_inputs = {}, False
+        self.logging = bool(kwargs.get("logging", False))
+        self.name = kwargs.get("name") or self._auto_name()
+
+    @classmethod
+    def _auto_name(cls):
+        kind = cls.__name__.lower()
+        return "%s_%d" % (kind, get_layer_uid(kind))
 
     def _call(self, inputs):
         return inputs
