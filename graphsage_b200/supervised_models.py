@@ -80,6 +80,94 @@ class _AggregateRowsFn(torch.autograd.Function):
         return (None, dsrc, None) + tuple(grads_w)
 
 
+def pool_branch_backward(pool, xn, h, hp, dhp, Wm, k, need_dx):
+    """Gradients through hp = pool_k(h), h = relu(xn @ Wm + bm) for one hop (reference aggregators.py:176-182 /
+    :256-262 backwards).  xn [n*k, F], h [n*k, hid] (post-ReLU), hp / dhp [n, hid].
+    max: the gradient of a maximum goes to the positions that attain it, split evenly among ties (TensorFlow's
+    reduce_max gradient); mean: dhp / k to every position.  Returns (dWm, dbm, dxn or None)."""
+    n, hid = hp.shape
+    h3 = h.reshape(n, k, hid)
+    if pool == "max":
+        sel = h3 == hp.unsqueeze(1)
+        share = dhp / sel.sum(dim=1).to(dhp.dtype)
+        dh = sel.to(dhp.dtype) * share.unsqueeze(1)
+    else:
+        dh = (dhp / float(k)).unsqueeze(1).expand(n, k, hid)
+    dpre = (dh * (h3 > 0).to(dhp.dtype)).reshape(n * k, hid)             # ReLU of the Dense layer
+    dWm = xn.t() @ dpre
+    dbm = dpre.sum(dim=0)
+    return dWm, dbm, (dpre @ Wm.t() if need_dx else None)
+
+
+class _PoolAggregateRowsFn(torch.autograd.Function):
+    """y = agg.aggregate_rows(src, segments) for MaxPoolingAggregator / MeanPoolingAggregator on the unfused fp32 path
+    (gather -> Dense(relu, bias) -> pool over the fanout -> both matmuls), differentiable w.r.t. the four weight tensors
+    and (layers >= 1) src.  The gathered neighbour rows and the MLP activations are kept for the backward pass."""
+
+    @staticmethod
+    def forward(ctx, agg, src, segments, Ws, Wn, Wm, bm):
+        code, post = act_code(agg.act)
+        if post is not None:
+            raise NotImplementedError("training supports act=relu or identity")
+        if len(agg.mlp_layers) != 1 or agg.dropout:
+            raise NotImplementedError("training supports one MLP layer and dropout = 0")
+        F_in, hid = src.shape[1], agg.hidden_dim
+        rows = max(s.out_row0 + s.n for s in segments)
+        with torch.no_grad():
+            xs = torch.empty((rows, ops.pad_cols(F_in)), dtype=torch.float32, device=src.device)[:, :F_in]
+            hp = torch.empty((rows, hid), dtype=torch.float32, device=src.device)
+            kept = []
+            for s in segments:
+                n, k = s.n, s.k
+                xn = ops.gather_rows(src, s.neigh_ids[:n * k]) if s.neigh_ids is not None else \
+                    src[s.neigh_row0:s.neigh_row0 + n * k]
+                mlp = agg.mlp_layers[0]
+                mlp.math = agg.math
+                h = mlp(xn)
+                if agg.pool == "mean":
+                    hp[s.out_row0:s.out_row0 + n] = ops.gather_mean(h, [ops.Seg(n, k)], want_self=False, out_pitch=hid)[1]
+                else:
+                    hp[s.out_row0:s.out_row0 + n] = ops.segment_max(h, n, k)
+                if s.self_ids is not None:
+                    ops.gather_rows(src, s.self_ids[:n], out=xs[s.out_row0:s.out_row0 + n])
+                else:
+                    xs[s.out_row0:s.out_row0 + n] = src[s.self_row0:s.self_row0 + n]
+                kept.extend([xn, h])
+            y = agg._finish([(xs, agg.input_dim, Ws), (hp, hid, Wn)], agg._combine())
+        ctx.pool, ctx.relu, ctx.concat = agg.pool, code == ops.ACT_RELU, bool(agg.concat)
+        ctx.segments, ctx.src_shape, ctx.F_in = segments, tuple(src.shape), F_in
+        ctx.src_needs_grad = bool(torch.is_tensor(src) and src.requires_grad)
+        ctx.save_for_backward(xs, hp, y, Ws, Wn, Wm, *kept)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xs, hp, y, Ws, Wn, Wm = ctx.saved_tensors[:6]
+        kept = ctx.saved_tensors[6:]
+        F_in = ctx.F_in
+        dz = dy * (y > 0).to(dy.dtype) if ctx.relu else dy
+        D = Ws.shape[1]
+        dz_s, dz_n = (dz[:, :D], dz[:, D:]) if ctx.concat else (dz, dz)
+        dWs, dWn = xs.t() @ dz_s, hp.t() @ dz_n
+        dhp = dz_n @ Wn.t()
+        dWm, dbm = torch.zeros_like(Wm), torch.zeros(Wm.shape[1], dtype=dy.dtype, device=dy.device)
+        dsrc = torch.zeros(ctx.src_shape, dtype=dy.dtype, device=dy.device) if ctx.src_needs_grad else None
+        dxs = dz_s @ Ws.t() if ctx.src_needs_grad else None
+        for i, s in enumerate(ctx.segments):
+            n, k = s.n, s.k
+            rows = slice(s.out_row0, s.out_row0 + n)
+            xn, h = kept[2 * i][:, :F_in], kept[2 * i + 1]
+            g_wm, g_bm, dxn = pool_branch_backward(ctx.pool, xn, h, hp[rows], dhp[rows], Wm, k, ctx.src_needs_grad)
+            dWm += g_wm
+            dbm += g_bm
+            if ctx.src_needs_grad:
+                if s.self_ids is not None or s.neigh_ids is not None:
+                    raise NotImplementedError("gradient w.r.t. an id-addressed source (trainable features) is out of scope")
+                dsrc[s.neigh_row0:s.neigh_row0 + n * k] += dxn
+                dsrc[s.self_row0:s.self_row0 + n] += dxs[rows]
+        return None, dsrc, None, dWs, dWn, dWm, dbm
+
+
 def differentiable_outputs(model, batch, normalize=True):
     """sample -> aggregate (-> l2_normalize) with an autograd graph over the aggregator weights; `model` is a
     SampleAndAggregate whose .aggregators exist (reference models.py:347-350 / supervised_models.py:79-85)."""
@@ -104,8 +192,13 @@ def differentiable_outputs(model, batch, normalize=True):
                 segs.append(ops.Seg(counts[hop], k, self_row0=row0[hop], neigh_row0=row0[hop + 1],
                                     out_row0=row0[hop]))
         agg = model.aggregators[layer]
-        ws = (agg.vars["weights"],) if "weights" in agg.vars else (agg.vars["self_weights"], agg.vars["neigh_weights"])
-        src = _AggregateRowsFn.apply(agg, src, segs, *ws)
+        if hasattr(agg, "mlp_layers"):                      # max-pool / mean-pool
+            mlp = agg.mlp_layers[0].vars
+            src = _PoolAggregateRowsFn.apply(agg, src, segs, agg.vars["self_weights"], agg.vars["neigh_weights"],
+                                             mlp["weights"], mlp["bias"])
+        else:
+            ws = (agg.vars["weights"],) if "weights" in agg.vars else (agg.vars["self_weights"], agg.vars["neigh_weights"])
+            src = _AggregateRowsFn.apply(agg, src, segs, *ws)
     out = src[:counts[0]]
     if normalize:
         out = out / torch.sqrt(torch.clamp((out * out).sum(dim=1, keepdim=True), min=1e-12))   # tf.nn.l2_normalize
@@ -119,9 +212,19 @@ def build_aggregators(model):
     for layer in range(L):
         dim_mult = 2 if model.concat and layer != 0 else 1
         act = identity if layer == L - 1 else relu
+        extra = {"model_size": model.model_size} if hasattr(model.aggregator_cls, "pool") else {}
         aggs.append(model.aggregator_cls(dim_mult * model.dims[layer], model.dims[layer + 1], act=act, dropout=0.,
-                                         concat=model.concat, device=model.device))
+                                         concat=model.concat, device=model.device, **extra))
     return aggs
+
+
+def aggregator_parameters(aggregators):
+    """(all trainable tensors, the subset the reference applies weight decay to).  The reference decays
+    `aggregator.vars` only (supervised_models.py:103-105, models.py:385-387) - the pooling aggregators' Dense variables
+    live in `mlp_layers[0].vars` and are trained but not decayed."""
+    decayed = [v for a in aggregators for v in a.vars.values()]
+    extra = [v for a in aggregators for layer in getattr(a, "mlp_layers", []) for v in layer.vars.values()]
+    return decayed + extra, decayed
 
 
 def classification_loss(logits, labels, sigmoid_loss):
@@ -152,8 +255,8 @@ class SupervisedGraphsage(SampleAndAggregate):
         super(SupervisedGraphsage, self).__init__(placeholders, features, adj, degrees, layer_infos, concat=concat,
                                                   aggregator_type=aggregator_type, model_size=model_size,
                                                   identity_dim=identity_dim, device=device, **kwargs)
-        if aggregator_type not in ("mean", "gcn"):
-            raise NotImplementedError("training is implemented for the mean and gcn aggregators")
+        if aggregator_type not in ("mean", "gcn", "maxpool", "meanpool"):
+            raise NotImplementedError("training is implemented for the mean, gcn, maxpool and meanpool aggregators")
         self.num_classes = num_classes
         self.sigmoid_loss = sigmoid_loss
         self.learning_rate, self.weight_decay = learning_rate, weight_decay
@@ -170,11 +273,10 @@ class SupervisedGraphsage(SampleAndAggregate):
         self.optimizer = torch.optim.Adam(self.parameters(), lr=self.learning_rate)      # TF AdamOptimizer defaults
 
     def parameters(self):
-        ps = []
-        for a in self.aggregators:
-            ps.extend(a.vars.values())
-        ps.extend(self.node_pred_vars.values())
-        return ps
+        return aggregator_parameters(self.aggregators)[0] + list(self.node_pred_vars.values())
+
+    def decayed_parameters(self):
+        return aggregator_parameters(self.aggregators)[1] + list(self.node_pred_vars.values())
 
     def outputs(self, batch):
         """l2-normalised node representations, differentiable (supervised_models.py:79-85)."""
@@ -190,7 +292,7 @@ class SupervisedGraphsage(SampleAndAggregate):
         labels = labels.to(device=logits.device, dtype=torch.float32)
         loss = classification_loss(logits, labels, self.sigmoid_loss)
         if self.weight_decay:
-            loss = loss + weight_decay_term(self.parameters(), self.weight_decay)
+            loss = loss + weight_decay_term(self.decayed_parameters(), self.weight_decay)
         return loss
 
     def train_step(self, batch, labels):

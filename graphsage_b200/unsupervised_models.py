@@ -12,7 +12,7 @@ import torch
 from . import ops
 from .models import SampleAndAggregate
 from .prediction import BipartiteEdgePredLayer, mrr_from_affinities
-from .supervised_models import build_aggregators, differentiable_outputs
+from .supervised_models import aggregator_parameters, build_aggregators, differentiable_outputs, weight_decay_term
 
 
 class UnigramNegativeSampler(object):
@@ -39,8 +39,8 @@ class UnsupervisedGraphsage(SampleAndAggregate):
         super(UnsupervisedGraphsage, self).__init__(placeholders, features, adj, degrees, layer_infos, concat=concat,
                                                     aggregator_type=aggregator_type, model_size=model_size,
                                                     identity_dim=identity_dim, device=device, **kwargs)
-        if aggregator_type not in ("mean", "gcn"):
-            raise NotImplementedError("training is implemented for the mean and gcn aggregators")
+        if aggregator_type not in ("mean", "gcn", "maxpool", "meanpool"):
+            raise NotImplementedError("training is implemented for the mean, gcn, maxpool and meanpool aggregators")
         self.neg_sample_size, self.neg_sample_weights = int(neg_sample_size), float(neg_sample_weights)
         self.learning_rate, self.weight_decay = learning_rate, weight_decay
         self.neg_sampler = UnigramNegativeSampler(degrees, 0.75, seed, device)      # models.py:336-343
@@ -54,7 +54,10 @@ class UnsupervisedGraphsage(SampleAndAggregate):
         self.optimizer = torch.optim.Adam(self.parameters(), lr=self.learning_rate)
 
     def parameters(self):
-        return [v for a in self.aggregators for v in a.vars.values()]
+        return aggregator_parameters(self.aggregators)[0]
+
+    def decayed_parameters(self):
+        return aggregator_parameters(self.aggregators)[1]
 
     def embed(self, batch):
         return differentiable_outputs(self, batch)                                   # models.py:347-370
@@ -71,8 +74,7 @@ class UnsupervisedGraphsage(SampleAndAggregate):
         o1, o2, on, _ = self._passes(batch1, batch2)
         loss = self.link_pred_layer.loss(o1, o2, on)
         if self.weight_decay:
-            for p in self.parameters():
-                loss = loss + self.weight_decay * 0.5 * (p * p).sum()
+            loss = loss + weight_decay_term(self.decayed_parameters(), self.weight_decay)       # models.py:385-387
         with torch.no_grad():
             self._last = (self.link_pred_layer.affinity(o1, o2), self.link_pred_layer.neg_cost(o1, on))
         return loss / float(o1.shape[0])
