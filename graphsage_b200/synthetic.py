@@ -55,3 +55,42 @@ def reddit_like(n=232965, f=602, max_degree=128, seed=123, with_features=True, m
         feats[:n] = rs.standard_normal((n, f)).astype(np.float32)
         out["features"] = feats
     return out
+
+
+def rmat_csr(scale, edge_factor=20, a=0.57, b=0.19, c=0.19, d=0.05, n_nodes=None, seed=123, undirected=False,
+             chunk=1 << 24):
+    """R-MAT graph (a, b, c, d = 0.57, 0.19, 0.19, 0.05; scale 27 trimmed to 10^8 nodes,
+    about 20 directed entries per node) as CSR over nodes 0..n-1 with sorted, de-duplicated rows and no self loops.
+
+    Each of the `edge_factor * n` directed edges picks one quadrant per bit level with probabilities (a, b, c, d); ids
+    that fall beyond `n_nodes` (when 2^scale is trimmed) are redrawn by folding (id mod n_nodes).  Generated in chunks
+    so the peak host memory stays bounded; deterministic for a given (scale, edge_factor, seed)."""
+    assert abs(a + b + c + d - 1.0) < 1e-9
+    n = int(n_nodes) if n_nodes is not None else 1 << scale
+    m = int(edge_factor) * n
+    rs = np.random.RandomState(seed)
+    keys = []
+    done = 0
+    while done < m:
+        cnt = min(chunk, m - done)
+        src = np.zeros(cnt, dtype=np.int64)
+        dst = np.zeros(cnt, dtype=np.int64)
+        for _ in range(scale):
+            r = rs.random_sample(cnt)
+            right = (r >= a) & (r < a + b) | (r >= a + b + c)          # quadrants b and d: destination bit set
+            down = r >= a + b                                            # quadrants c and d: source bit set
+            src = (src << 1) | down
+            dst = (dst << 1) | right
+        if n != (1 << scale):
+            src %= n
+            dst %= n
+        keep = src != dst
+        src, dst = src[keep], dst[keep]
+        if undirected:
+            src, dst = np.concatenate([src, dst]), np.concatenate([dst, src])
+        keys.append(src * n + dst)
+        done += cnt
+    key = np.unique(np.concatenate(keys))
+    rows, cols = key // n, (key % n).astype(np.int32)
+    indptr = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=n))]).astype(np.int64)
+    return indptr, cols

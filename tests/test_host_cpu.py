@@ -105,3 +105,23 @@ def test_padded_from_csr_fast_properties():
     fwd = set(zip(a[:2000].tolist(), indices[:2000].tolist()))
     allp = set(zip(a.tolist(), indices.tolist()))
     assert all((v, u) in allp for (u, v) in fwd)
+
+
+def test_rmat_generator_properties():
+    from graphsage_b200.synthetic import rmat_csr
+    indptr, indices = rmat_csr(12, edge_factor=8, seed=5)
+    n = 1 << 12
+    assert indptr.shape == (n + 1,) and indptr[0] == 0 and indptr[-1] == len(indices) and indices.dtype == np.int32
+    deg = np.diff(indptr)
+    assert 0.5 * 8 * n < len(indices) <= 8 * n                    # duplicates and self loops removed
+    for u in (0, 1, 17, n - 1):                                   # sorted, unique, no self loop
+        row = indices[indptr[u]:indptr[u + 1]]
+        assert np.all(np.diff(row) > 0) and u not in row
+    assert deg.max() > 20 * deg.mean()                            # the skew R-MAT is used for
+    assert deg[:n // 2].sum() > 2.5 * deg[n // 2:].sum()          # a + b = 0.76 of the mass on the low half of the sources
+    again = rmat_csr(12, edge_factor=8, seed=5)
+    assert np.array_equal(again[0], indptr) and np.array_equal(again[1], indices)
+    ip2, ix2 = rmat_csr(12, edge_factor=8, seed=5, n_nodes=3000, undirected=True, chunk=5000)
+    assert ip2.shape == (3001,) and ix2.max() < 3000
+    und = set(zip(np.repeat(np.arange(3000), np.diff(ip2)).tolist(), ix2.tolist()))
+    assert all((v, u) in und for (u, v) in list(und)[:2000])      # symmetric
