@@ -353,10 +353,13 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
 // stage's mbarrier transaction count.  No per-thread cp.async group waits, no generic->async proxy fence, no per-warp
 // arrive: what remains per stage is one empty-barrier wait, one expect_tx and one gather4 per lane (32 lanes x 4 rows =
 // the 128-row stage).  ptxas serialises the 32 lanes of an instruction with per-lane operands (ELECT waterfall), so
-// MP_G4_WARPS producer warps take K-blocks round-robin - each warp fills whole stages - to keep that latency off the
-// critical path.  Columns >= K and rows named n_rows (tile padding) are out of bounds for the tensor map: zero-filled.
+// there is one producer warp PER RING SLOT, each filling whole stages, to keep that latency off the critical path.
+// Producer warp w owns slot w and fills K-blocks w, w + MP_SA, ... in order: a warp that served several slots could get
+// two fills ahead of a slot it last touched long ago, and an mbarrier wait only carries ONE parity bit - it would pass on
+// the stale phase and overwrite a stage that has not been consumed (tools/pipeline_model.py reproduces exactly that for
+// 8 warps over 7 slots; with one warp per slot every wait is at most one phase ahead).
+// Columns >= K and rows named n_rows (tile padding) are out of bounds for the tensor map: zero-filled.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int MP_G4_WARPS = 8;
 
 __device__ __forceinline__ void tma_gather4(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int col, int r0, int r1,
                                             int r2, int r3) {
@@ -368,8 +371,9 @@ __device__ __forceinline__ void tma_gather4(void* smem_dst, const CUtensorMap* t
 }
 
 template <int MP_SA>
-__global__ void __launch_bounds__((MP_G4_WARPS + 6) * 32, 1)
+__global__ void __launch_bounds__((MP_SA + 6) * 32, 1)
     maxpool_mlp_g4_kernel(const __grid_constant__ MpParams prm, const __grid_constant__ CUtensorMap tmap) {
+  constexpr int MP_G4_WARPS = MP_SA;              // one producer warp per ring slot (see above)
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_a[MP_SA], empty_a[MP_SA], acc_full[2], acc_empty[2], b_full;
   __shared__ uint32_t tmem_base_smem;
@@ -432,9 +436,10 @@ __global__ void __launch_bounds__((MP_G4_WARPS + 6) * 32, 1)
     while (kb >= kblocks) { kb -= kblocks; ++tl; }
     load_ids(tl, cur);
     load_ids(tl + 1, nxt);
-    for (int64_t it = warp; it < total_it; it += MP_G4_WARPS) {
-      const int s = (int)(it % MP_SA);
-      mbar_wait(&empty_a[s], ((uint32_t)(it / MP_SA) & 1u) ^ 1u);
+    const int s = warp;                             // this warp's slot
+    uint32_t fill = 0;                              // fills of the slot so far
+    for (int64_t it = warp; it < total_it; it += MP_G4_WARPS, ++fill) {
+      mbar_wait(&empty_a[s], (fill & 1u) ^ 1u);
       if (lane == 0) mbar_expect_tx(&full_a[s], (uint32_t)MP_IMG);
       __syncwarp();
       tma_gather4(a_ring + (size_t)s * MP_IMG + lane * 256, &tmap, &full_a[s], kb * MP_KCOLS, cur[0], cur[1], cur[2], cur[3]);
@@ -497,9 +502,10 @@ __device__ __forceinline__ void tma_gather4_multicast(void* smem_dst, const CUte
 }
 
 template <int MP_SA, int CL>
-__global__ void __launch_bounds__((MP_G4_WARPS + 6) * 32, 1)
+__global__ void __launch_bounds__((MP_SA + 6) * 32, 1)
     maxpool_mlp_g4mc_kernel(const __grid_constant__ MpParams prm, const __grid_constant__ CUtensorMap tmap) {
   static_assert(CL == 2 || CL == 4, "cluster = the 2 or 4 hidden slices of one M tile");
+  constexpr int MP_G4_WARPS = MP_SA;              // one producer warp per ring slot (see the gather4 variant)
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_a[MP_SA], empty_a[MP_SA], acc_full[2], acc_empty[2], b_full;
   __shared__ uint32_t tmem_base_smem;
@@ -567,9 +573,10 @@ __global__ void __launch_bounds__((MP_G4_WARPS + 6) * 32, 1)
     while (kb >= kblocks) { kb -= kblocks; ++tl; }
     load_ids(tl, cur);
     load_ids(tl + 1, nxt);
-    for (int64_t it = warp; it < total_it; it += MP_G4_WARPS) {
-      const int s = (int)(it % MP_SA);
-      mbar_wait(&empty_a[s], ((uint32_t)(it / MP_SA) & 1u) ^ 1u);      // every CTA of the cluster has consumed the stage
+    const int s = warp;                             // this warp's slot
+    uint32_t fill = 0;                              // fills of the slot so far
+    for (int64_t it = warp; it < total_it; it += MP_G4_WARPS, ++fill) {
+      mbar_wait(&empty_a[s], (fill & 1u) ^ 1u);     // every CTA of the cluster has consumed the previous fill
       if (lane == 0) mbar_expect_tx(&full_a[s], (uint32_t)MP_IMG);
       __syncwarp();
       if (lane < LANES)
@@ -712,7 +719,7 @@ static int32_t pool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K,
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)ctas);                      // a multiple of n_slices: whole clusters
-    cfg.blockDim = dim3((gs::MP_G4_WARPS + 6) * 32);
+    cfg.blockDim = dim3((unsigned)(((sa7 ? 7 : 6) + 6) * 32));
     cfg.dynamicSmemBytes = gs::MP_SMEM;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr;
@@ -737,11 +744,10 @@ static int32_t pool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K,
     CUtensorMap tmap;
     const int32_t rc = make_table_tensor_map(&tmap, table_bf16, n_rows, K, pitch);
     if (rc != GS_OK) return rc;
-    const unsigned threads = (gs::MP_G4_WARPS + 6) * 32;
     if (prm.kblocks <= gs::MP_RING - 7)
-      gs::maxpool_mlp_g4_kernel<7><<<(unsigned)ctas, threads, gs::MP_SMEM, (cudaStream_t)stream>>>(prm, tmap);
+      gs::maxpool_mlp_g4_kernel<7><<<(unsigned)ctas, (7 + 6) * 32, gs::MP_SMEM, (cudaStream_t)stream>>>(prm, tmap);
     else
-      gs::maxpool_mlp_g4_kernel<6><<<(unsigned)ctas, threads, gs::MP_SMEM, (cudaStream_t)stream>>>(prm, tmap);
+      gs::maxpool_mlp_g4_kernel<6><<<(unsigned)ctas, (6 + 6) * 32, gs::MP_SMEM, (cudaStream_t)stream>>>(prm, tmap);
     return gs::launch_check("maxpool_mlp_g4_kernel");
   }
   if (prm.kblocks <= gs::MP_RING - 7)

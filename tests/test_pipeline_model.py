@@ -1,0 +1,17 @@
+"""The K4 stage hand-off protocol (tools/pipeline_model.py): slot / parity arithmetic of the default kernel and of the
+two TMA gather4 variants, under a random scheduler.  CPU only; guards the arithmetic the kernels share with the model."""
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+
+import pipeline_model as pm  # noqa: E402
+
+
+def test_handoff_protocols_are_live_and_alias_free():
+    assert pm.sweep(seeds=2) == 2 * 5 * 2 * 4
+
+
+def test_model_rejects_more_stage_filling_warps_than_slots():
+    msg = pm.shows_the_aliasing_bug()
+    assert msg is not None and ("aliasing" in msg or "refilled" in msg or "expected" in msg)
