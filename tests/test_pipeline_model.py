@@ -15,3 +15,10 @@ def test_handoff_protocols_are_live_and_alias_free():
 def test_model_rejects_more_stage_filling_warps_than_slots():
     msg = pm.shows_the_aliasing_bug()
     assert msg is not None and ("aliasing" in msg or "refilled" in msg or "expected" in msg)
+
+
+def test_gather4_producer_tile_walk_matches_direct_indexing():
+    for sa in (6, 7):
+        for kblocks in (1, 2, 3, 5, 6, 7, 8, 13, 19, 20):
+            for tiles in (1, 2, 5, 14):
+                assert pm.check_producer_walk(sa, kblocks, tiles)

@@ -170,3 +170,33 @@ def shows_the_aliasing_bug():
 if __name__ == "__main__":
     print("hand-off protocol model: %d simulations, no deadlock / aliasing / early refill / misordered K-block" % sweep())
     print("8 warps over 7 slots ->", shows_the_aliasing_bug())
+
+
+def check_producer_walk(sa, kblocks, tiles):
+    """The gather4 producers' incremental (tile, K-block) walk and their current / next-tile row-id registers
+    (maxpool_mlp_g4_kernel: kb += MP_SA; while (kb >= kblocks) ...; adv == 1 -> cur = nxt) against the direct
+    it // kblocks, it % kblocks.  `load` records which tile's ids a register set holds."""
+    total = kblocks * tiles
+    for warp in range(sa):
+        tl, kb = 0, warp
+        while kb >= kblocks:
+            kb -= kblocks
+            tl += 1
+        cur, nxt = tl, tl + 1                       # load_ids(tl, cur); load_ids(tl + 1, nxt)
+        it = warp
+        while it < total:
+            assert (cur, kb) == (it // kblocks, it % kblocks), (sa, kblocks, warp, it, cur, kb)
+            kb += sa
+            adv = 0
+            while kb >= kblocks:
+                kb -= kblocks
+                adv += 1
+            if adv == 1:
+                cur = nxt
+                tl += 1
+                nxt = tl + 1
+            elif adv > 1:
+                tl += adv
+                cur, nxt = tl, tl + 1
+            it += sa
+    return True
