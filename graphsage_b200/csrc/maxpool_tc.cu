@@ -358,7 +358,8 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
 // two fills ahead of a slot it last touched long ago, and an mbarrier wait only carries ONE parity bit - it would pass on
 // the stale phase and overwrite a stage that has not been consumed (tools/pipeline_model.py reproduces exactly that for
 // 8 warps over 7 slots; with one warp per slot every wait is at most one phase ahead).
-// Columns >= K and rows named n_rows (tile padding) are out of bounds for the tensor map: zero-filled.
+// Columns >= K are out of bounds for the tensor map and zero-filled by the TMA; tile rows past the last fanout group
+// (never read by the epilogue) fetch row 0.
 // ---------------------------------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ void tma_gather4(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int col, int r0, int r1,
@@ -415,7 +416,7 @@ __global__ void __launch_bounds__((MP_SA + 6) * 32, 1)
     const int64_t total_rows = prm.n_groups * prm.k;
     const int64_t my_tiles = tile0 < prm.n_tiles ? (prm.n_tiles - tile0 + tile_step - 1) / tile_step : 0;
     const int64_t total_it = my_tiles * kblocks;
-    const int oob_row = (int)prm.n_rows;            // out of bounds for the tensor map: the TMA writes zeros
+    const int pad_row = 0;                          // tile rows past the last group: never read by the epilogue, any valid row will do
     int cur[4], nxt[4];                             // table rows of this lane's tile rows 4 lane .. 4 lane + 3
     auto load_ids = [&](int64_t tl, int (&ids)[4]) {
       const int64_t t = tile0 + tl * tile_step;
@@ -423,7 +424,7 @@ __global__ void __launch_bounds__((MP_SA + 6) * 32, 1)
       for (int i = 0; i < 4; ++i) {
         const int r = 4 * lane + i;
         const int64_t flat = t * rows_valid + r;    // index into the (group, j) row list
-        int64_t id = oob_row;
+        int64_t id = pad_row;
         if (tl < my_tiles && r < rows_valid && flat < total_rows) {
           id = prm.row_ids ? (int64_t)prm.row_ids[flat] : prm.row0 + flat;
           if (id < 0 || id >= prm.n_rows) id = prm.n_rows - 1;
@@ -551,7 +552,7 @@ __global__ void __launch_bounds__((MP_SA + 6) * 32, 1)
     const int64_t total_rows = prm.n_groups * prm.k;
     const int64_t my_tiles = tile0 < prm.n_tiles ? (prm.n_tiles - tile0 + tile_step - 1) / tile_step : 0;
     const int64_t total_it = my_tiles * kblocks;
-    const int oob_row = (int)prm.n_rows;            // out of bounds for the tensor map: the TMA writes zeros
+    const int pad_row = 0;                          // tile rows past the last group: never read by the epilogue, any valid row will do
     const int row_base = rank * ROWS_PER_CTA + 4 * lane;
     int cur[4], nxt[4];
     auto load_ids = [&](int64_t tl, int (&ids)[4]) {
@@ -560,7 +561,7 @@ __global__ void __launch_bounds__((MP_SA + 6) * 32, 1)
       for (int i = 0; i < 4; ++i) {
         const int r = row_base + i;
         const int64_t flat = t * rows_valid + r;
-        int64_t id = oob_row;
+        int64_t id = pad_row;
         if (lane < LANES && tl < my_tiles && r < rows_valid && flat < total_rows) {
           id = prm.row_ids ? (int64_t)prm.row_ids[flat] : prm.row0 + flat;
           if (id < 0 || id >= prm.n_rows) id = prm.n_rows - 1;
