@@ -14,7 +14,7 @@ CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libgraphsage_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--use_fast_math" if False else "-DGS_NO_FAST_MATH"]
+         "-Xcompiler", "-fPIC", "-DGS_NO_FAST_MATH"] + os.environ.get("GS_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _sources():

@@ -96,6 +96,24 @@ __device__ __forceinline__ void mp_stamp(uint32_t tcount, int slot) {
   }
 }
 
+// Optional epilogue cycle breakdown (build with GS_EXTRA_NVCC_FLAGS=-DGS_K4_EPI_PROBE; compiled out otherwise):
+// CTA 0, epilogue thread 0 accumulates clock64 deltas into g_mp_dbg[100..105] =
+// {tmem ld + wait, staging stores, barrier 1, pooling loop + global stores, barrier 2, column blocks counted}
+#ifdef GS_K4_EPI_PROBE
+#define MP_EPI_T(var) const long long var = clock64()
+#define MP_EPI_ACC(slot, a, b) \
+  do {                         \
+    if (blockIdx.x == 0 && et == 0) g_mp_dbg[100 + (slot)] += (unsigned long long)((b) - (a)); \
+  } while (0)
+#else
+#define MP_EPI_T(var) \
+  do {                \
+  } while (0)
+#define MP_EPI_ACC(slot, a, b) \
+  do {                         \
+  } while (0)
+#endif
+
 // ---- roles shared by the kernel variants (forced inline: one copy of the logic, no call overhead) ----
 
 // MMA issuer warp: waits for each A stage, issues the two K = 16 MMAs of the K-block against the resident weights,
@@ -181,14 +199,18 @@ __device__ __forceinline__ void mp_epilogue_role(const MpParams& prm, int et, in
 #pragma unroll 1
     for (int cb = 0; cb < 4; ++cb) {
       uint32_t r[32];
+      MP_EPI_T(e0);
       tmem_ld_32x32(tmem_acc + (uint32_t)(cb * 32), r);
       tmem_ld_wait();
+      MP_EPI_T(e1);
       const int hcol0 = slice * 128 + cb * 32;
       // raw accumulators go to the staging tile; bias and ReLU are applied AFTER the max
       // (max_j relu(x_j + b) == relu(max_j x_j + b): b is per column, relu is monotone)
 #pragma unroll
       for (int j = 0; j < 32; ++j) stage[j * MP_STAGE_LD + row] = __uint_as_float(r[j]);
+      MP_EPI_T(e2);
       named_bar_sync(1, 128);
+      MP_EPI_T(e3);
       // thread = (column cc, group residue): max over each group's k consecutive rows, 8 independent
       // shared loads per batch
       {
@@ -221,7 +243,15 @@ __device__ __forceinline__ void mp_epilogue_role(const MpParams& prm, int et, in
           }
         }
       }
+      MP_EPI_T(e4);
       named_bar_sync(1, 128);
+      MP_EPI_T(e5);
+      MP_EPI_ACC(0, e0, e1);
+      MP_EPI_ACC(1, e1, e2);
+      MP_EPI_ACC(2, e2, e3);
+      MP_EPI_ACC(3, e3, e4);
+      MP_EPI_ACC(4, e4, e5);
+      MP_EPI_ACC(5, 0, 1);
     }
     tc_fence_before();
     __syncwarp();

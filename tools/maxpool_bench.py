@@ -38,3 +38,9 @@ for tc in range(3, 7):
 
 n = max(1, buf[104])
 print("producer step cycles (avg over %d K-blocks): wait %.0f  stores %.0f  fence %.0f  arrive %.0f" % (n, buf[100]/n, buf[101]/n, buf[102]/n, buf[103]/n))
+
+if buf[105]:          # built with GS_EXTRA_NVCC_FLAGS=-DGS_K4_EPI_PROBE
+    nb = buf[105]
+    print("epilogue cycles per 32-column block (avg over %d): tmem ld %.0f  staging stores %.0f  barrier %.0f  pooling + stores %.0f  "
+          "barrier %.0f" % (nb, buf[100] / nb, buf[101] / nb, buf[102] / nb, buf[103] / nb, buf[104] / nb))
+
