@@ -11,6 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libgraphsage_b200.so")
 
+ABI_VERSION = 2          # GS_ABI_VERSION of include/graphsage_b200.h this binding was written against
 GS_F32, GS_BF16 = 0, 1
 ACT_NONE, ACT_RELU = 0, 1
 COMBINE_ADD, COMBINE_CONCAT = 0, 1
@@ -29,8 +30,8 @@ MAX_SHARDS = 16
 
 
 class ShardedTable(ctypes.Structure):
-    _fields_ = [("base", c_vp * MAX_SHARDS), ("n_shards", c_i32), ("my_shard", c_i32), ("rows_per_shard", c_i64),
-                ("n_global_rows", c_i64)]
+    _fields_ = [("base", c_vp * MAX_SHARDS), ("row_start", c_i64 * (MAX_SHARDS + 1)), ("n_shards", c_i32),
+                ("my_shard", c_i32), ("n_global_rows", c_i64), ("zero_row", c_i64), ("remap", c_vp)]
 
 
 class GemmPart(ctypes.Structure):
@@ -59,6 +60,8 @@ _SIGNATURES = {
     "gs_ipc_export": (c_i32, [c_vp, ctypes.c_char_p]),
     "gs_ipc_import": (c_i32, [ctypes.c_char_p, ctypes.POINTER(c_vp)]),
     "gs_ipc_close": (c_i32, [c_vp]),
+    "gs_gather_rows_f32": (c_i32, [c_vp, c_i32, c_i64, c_i32, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    "gs_cast_rows_bf16": (c_i32, [c_vp, c_i64, c_i32, c_i64, c_vp, c_i64, c_vp]),
     "gs_segment_max": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i64, c_vp, c_i64, c_vp]),
     "gs_sage_gemm_workspace_bytes": (c_i64, [c_i64, ctypes.POINTER(GemmPart), c_i32, c_i32]),
     "gs_sage_gemm": (c_i32, [c_i64, ctypes.POINTER(GemmPart), c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp,
@@ -93,6 +96,9 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(_lib, name)          # AttributeError = symbol not exported
             fn.restype, fn.argtypes = res, args
+        if _lib.gs_version() != ABI_VERSION:
+            raise ImportError("graphsage_b200: %s has ABI version %d, this binding needs %d - rebuild it"
+                              % (LIB_PATH, _lib.gs_version(), ABI_VERSION))
         for kv in os.environ.get("GS_TUNING", "").split(","):      # e.g. GS_TUNING=gather_variant=2,gather_ctas_per_sm=3
             if "=" in kv:
                 k, v = kv.split("=", 1)

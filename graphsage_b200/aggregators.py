@@ -47,8 +47,9 @@ class _SageAggregator(Layer):
         code, post = act_code(self.act)
         if (len(segments) != 1 or not torch.is_tensor(src) or post is not None or self.dropout
                 or segments[0].out_row0 + segments[0].n > ops.SMALL_LAYER_MAX_ROWS or src.shape[1] > 2048
-                or any(K != src.shape[1] for (_, K, _) in parts)):
-            return None
+                or any(K != src.shape[1] for (_, K, _) in parts)
+                or (sum(B.shape[1] for (_, _, B) in parts) if combine == ops.COMBINE_CONCAT else parts[0][2].shape[1]) > 1024):
+            return None       # gs_sage_layer_small limits: rows, K <= 2048, total output width <= 1024
         l2 = bool(final and final.get("l2_normalize"))
         bump = final.get("bump") if final else None
         y = ops.sage_layer_small(src, segments[0], parts, combine=combine, include_self=include_self,
@@ -97,7 +98,7 @@ class MeanAggregator(_SageAggregator):
         return self._finish([(self_vecs, self.input_dim, self.vars["self_weights"]),
                              (means, self.neigh_input_dim, self.vars["neigh_weights"])], self._combine())
 
-    def aggregate_rows(self, src, segments, final=None):
+    def aggregate_rows(self, src, segments, final=None, src_persistent=False):
         if self.dropout:
             raise NotImplementedError("dropout > 0 uses the dense call path")
         y = self._small_layer(src, segments, [(None, self.input_dim, self.vars["self_weights"]),
@@ -143,7 +144,7 @@ class GCNAggregator(_SageAggregator):
         _, means = ops.gather_mean(src, seg, include_self=True, want_self=False)
         return self._finish([(means, self.neigh_input_dim, self.vars["weights"])], ops.COMBINE_ADD)
 
-    def aggregate_rows(self, src, segments, final=None):
+    def aggregate_rows(self, src, segments, final=None, src_persistent=False):
         if self.dropout:
             raise NotImplementedError("dropout > 0 uses the dense call path")
         y = self._small_layer(src, segments, [(None, self.neigh_input_dim, self.vars["weights"])], ops.COMBINE_ADD, True,
@@ -205,15 +206,20 @@ class MaxPoolingAggregator(_SageAggregator):
         return self._finish([(self_vecs, self.input_dim, self.vars["self_weights"]),
                              (hmax, self.hidden_dim, self.vars["neigh_weights"])], self._combine())
 
-    def _bf16_table(self, src):
-        """bf16 copy of an fp32 source with a 16-byte-multiple row pitch (cached per source tensor version)."""
+    def _bf16_table(self, src, persistent):
+        """K4's operand table: bf16 rows with a 16-byte-multiple pitch.  A bf16 source is used as is.  An fp32 source is
+        cast by gs_cast_rows_bf16 - once per tensor version when the caller says it is the persistent feature table
+        (layer 0), on EVERY call otherwise: intermediate activations are fresh torch.empty buffers the C library
+        fills, so neither their address nor their _version tells one step's values from the next."""
         if src.dtype == torch.bfloat16:
+            if src.stride(0) % 8 != 0 or src.data_ptr() % 16 != 0:
+                raise ValueError("bfloat16 source rows must be 16-byte aligned multiples (pitch % 8 == 0)")
             return src
+        if not persistent:
+            return ops.cast_rows_bf16(src)
         key = (src.data_ptr(), src._version, tuple(src.shape))
-        if getattr(self, "_bf16_key", None) != key:
-            t = torch.zeros((src.shape[0], ops.pad_cols(src.shape[1])), dtype=torch.bfloat16, device=src.device)
-            t[:, :src.shape[1]] = src
-            self._bf16_src, self._bf16_key = t[:, :src.shape[1]], key
+        if getattr(self, "_bf16_ref", None) is not src or getattr(self, "_bf16_key", None) != key:
+            self._bf16_src, self._bf16_ref, self._bf16_key = ops.cast_rows_bf16(src), src, key
         return self._bf16_src
 
     def _fused_ok(self, src, segments):
@@ -221,27 +227,30 @@ class MaxPoolingAggregator(_SageAggregator):
                 and self.neigh_input_dim <= 640 and self.hidden_dim % 128 == 0 and all(s.k <= 128 for s in segments)
                 and self.mlp_layers[0].act is relu and "bias" in self.mlp_layers[0].vars)
 
-    def aggregate_rows(self, src, segments, final=None):
+    def aggregate_rows(self, src, segments, final=None, src_persistent=False):
         rows = max(s.out_row0 + s.n for s in segments)
         dev = src.device
         if self._fused_ok(src, segments):
-            # K4: gather -> MLP -> ReLU -> max over the fanout in one tcgen05 kernel per hop (bf16 operands)
-            table = self._bf16_table(src)
+            # K4: gather -> MLP -> ReLU -> max over the fanout in one tcgen05 kernel per hop (bf16 operands).
+            # Every launch of this branch is one of the library's kernels (no torch copy / convert kernels in the step).
+            table = self._bf16_table(src, src_persistent)
             if getattr(self, "_packed_mlp", None) is None:
                 self._packed_mlp = ops.PackedMlpWeights()
             mlp = self.mlp_layers[0]
             F_in = src.shape[1]
-            xs = torch.empty((rows, ops.pad_cols(F_in)), dtype=torch.float32, device=dev)[:, :F_in]
             hmax = torch.empty((rows, self.hidden_dim), dtype=torch.float32, device=dev)
             for s in segments:
-                n = s.n
-                ops.maxpool_mlp_fused(table, n, s.k, mlp.vars["weights"], mlp.vars["bias"], self._packed_mlp,
+                ops.maxpool_mlp_fused(table, s.n, s.k, mlp.vars["weights"], mlp.vars["bias"], self._packed_mlp,
                                       row_ids=s.neigh_ids, row0=s.neigh_row0, K=self.neigh_input_dim,
-                                      out=hmax[s.out_row0:s.out_row0 + n], pool=self.pool)
-                if s.self_ids is not None:
-                    xs[s.out_row0:s.out_row0 + n] = ops.gather_rows(src, s.self_ids[:n]).float()
-                else:
-                    xs[s.out_row0:s.out_row0 + n] = src[s.self_row0:s.self_row0 + n].float()
+                                      out=hmax[s.out_row0:s.out_row0 + s.n], pool=self.pool)
+            s0 = segments[0]
+            if len(segments) == 1 and s0.self_ids is None and s0.out_row0 == 0 and src.dtype == torch.float32:
+                xs = src[s0.self_row0:s0.self_row0 + s0.n]         # the self rows are already a dense fp32 row range
+            else:
+                xs = torch.empty((rows, ops.pad_cols(F_in)), dtype=torch.float32, device=dev)[:, :F_in]
+                for s in segments:
+                    ops.gather_rows_f32(src, ids=None if s.self_ids is None else s.self_ids[:s.n], row0=s.self_row0,
+                                        n=s.n, out=xs[s.out_row0:s.out_row0 + s.n])
             return self._finish([(xs, self.input_dim, self.vars["self_weights"]),
                                  (hmax, self.hidden_dim, self.vars["neigh_weights"])], self._combine())
         xs = torch.empty((rows, ops.pad_cols(src.shape[1])), dtype=torch.float32, device=dev)[:, :src.shape[1]]

@@ -190,6 +190,50 @@ __global__ void __launch_bounds__(192) gather_mean_tma_kernel(const float* __res
 }
 
 // ------------------------------------------------------------------------------------------
+// Row resolvers: where the feature row of a node id lives.
+//   DenseRows : one table in this GPU's HBM.
+//   ShardRows : node-partitioned table (multi-GPU).  Shard o owns the ids [row_start[o], row_start[o+1]) at
+//     base[o] (peer-mapped over NVLink for o != my_shard); this GPU additionally holds REPLICAS of the remote rows
+//     it reads most, addressed through `remap` (remap[id] >= 0: local row index inside base[my_shard]; -1: not
+//     held locally).  Ids outside [0, N) - the dummy id N included - read the local zero row.
+//     Remote rows are pulled by the consuming kernel itself: the halo exchange IS the gather.
+// ------------------------------------------------------------------------------------------
+struct DenseRows {
+  const float* src;
+  int64_t n_rows, pitch;
+  __device__ __forceinline__ const float* row(int64_t id) const { return src + clamp_row(id, n_rows) * pitch; }
+};
+
+struct ShardTab {
+  const float* base[GS_MAX_SHARDS];
+  int64_t row_start[GS_MAX_SHARDS + 1];
+  int32_t n_shards, my_shard;
+  int64_t n_global_rows;      // N + 1
+  int64_t zero_row;           // local row index of this GPU's all-zero row
+  const int32_t* remap;       // [N + 1] or NULL
+};
+
+struct ShardRows {
+  ShardTab t;
+  int64_t pitch;
+  __device__ __forceinline__ const float* row(int64_t id) const {
+    const float* mine = t.base[t.my_shard];
+    if (id < 0 || id >= t.n_global_rows - 1) return mine + t.zero_row * pitch;
+    if (t.remap) {
+      const int32_t s = __ldg(t.remap + id);
+      if (s >= 0) return mine + (int64_t)s * pitch;
+    } else if (id >= t.row_start[t.my_shard] && id < t.row_start[t.my_shard + 1]) {
+      return mine + (id - t.row_start[t.my_shard]) * pitch;
+    }
+    int o = 0;
+#pragma unroll
+    for (int q = 1; q < GS_MAX_SHARDS; ++q)
+      if (q < t.n_shards && id >= t.row_start[q]) o = q;
+    return t.base[o] + (id - t.row_start[o]) * pitch;
+  }
+};
+
+// ------------------------------------------------------------------------------------------
 // gather + mean, TMA bulk variant 2: the rows of an output node are fetched in GROUPS of up to
 // kGroupRows rows through a two-buffer ring, so the bulk copies of group t+1 are in flight while the
 // CTA sums group t (variant 1 alternates copy and sum inside a CTA and relies on co-resident CTAs
@@ -197,8 +241,9 @@ __global__ void __launch_bounds__(192) gather_mean_tma_kernel(const float* __res
 // ------------------------------------------------------------------------------------------
 constexpr int kGroupRows = 13;
 
-__global__ void __launch_bounds__(192) gather_mean_tma2_kernel(const float* __restrict__ src, int64_t n_src_rows, int F,
-                                                               int64_t pitch, const __grid_constant__ SegTable tab,
+template <class Rows>
+__global__ void __launch_bounds__(192) gather_mean_tma2_kernel(const __grid_constant__ Rows rows_of, int F,
+                                                               const __grid_constant__ SegTable tab,
                                                                int include_self, float* __restrict__ out_self,
                                                                float* __restrict__ out_mean, int64_t out_pitch,
                                                                int row_bytes) {
@@ -233,8 +278,7 @@ __global__ void __launch_bounds__(192) gather_mean_tma2_kernel(const float* __re
         int64_t id;
         if (jj < k) id = sg.neigh_ids ? (int64_t)sg.neigh_ids[i * k + jj] : sg.neigh_row0 + i * k + jj;
         else id = sg.self_ids ? (int64_t)sg.self_ids[i] : sg.self_row0 + i;
-        id = clamp_row(id, n_src_rows);
-        bulk_g2s(smem + buf * buf_bytes + (size_t)j * row_bytes, src + id * pitch, (uint32_t)row_bytes, &bar[buf]);
+        bulk_g2s(smem + buf * buf_bytes + (size_t)j * row_bytes, rows_of.row(id), (uint32_t)row_bytes, &bar[buf]);
       }
     }
     if (first + cnt >= rows_total) { r_issue += gridDim.x; g_issue = 0; } else { ++g_issue; }
@@ -354,6 +398,46 @@ __global__ void __launch_bounds__(256) gather_rows_simple_kernel(const T* __rest
   }
 }
 
+// rows of a bf16 (or fp32) table gathered straight into an fp32 matrix - the self rows of the bf16 max-pool path
+// (models.py:299 + the cast the fp32 self_weights contraction needs); one warp per row, pad columns zeroed
+template <typename T>
+__global__ void __launch_bounds__(256) gather_rows_to_f32_kernel(const T* __restrict__ src, int64_t n_rows, int F,
+                                                                 int64_t pitch, const int32_t* __restrict__ ids, int64_t row0,
+                                                                 int64_t n, float* __restrict__ out, int64_t out_pitch) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const int64_t id = clamp_row(ids ? (int64_t)ids[i] : row0 + i, n_rows);
+    for (int c = lane; c < (int)out_pitch; c += 32) {
+      float v = 0.f;
+      if (c < F) {
+        if constexpr (sizeof(T) == 2) v = __uint_as_float(((uint32_t)src[id * pitch + c]) << 16);   // bf16 -> fp32 (exact)
+        else v = src[id * pitch + c];
+      }
+      out[i * out_pitch + c] = v;
+    }
+  }
+}
+
+// fp32 [n, F] -> bf16 [n, out_pitch] (round to nearest even, pad columns zeroed): the layer-(l+1) source of the
+// bf16 max-pool path
+__global__ void __launch_bounds__(256) cast_rows_bf16_kernel(const float* __restrict__ x, int64_t n, int F, int64_t ldx,
+                                                             uint16_t* __restrict__ out, int64_t out_pitch) {
+  const int64_t total = n * out_pitch;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = q / out_pitch;
+    const int c = (int)(q - i * out_pitch);
+    uint16_t h = 0;
+    if (c < F) {
+      const uint32_t u = __float_as_uint(x[i * ldx + c]);
+      if ((u & 0x7fffffffu) > 0x7f800000u) h = (uint16_t)((u >> 16) | 0x40u);          // NaN stays NaN
+      else h = (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+    }
+    out[q] = h;
+  }
+}
+
 __global__ void __launch_bounds__(256) segment_max_kernel(const float* __restrict__ x, int64_t n, int k, int C,
                                                           int64_t ldx, float* __restrict__ out, int64_t ldo) {
   for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
@@ -388,20 +472,8 @@ __global__ void __launch_bounds__(256) l2_normalize_kernel(float* __restrict__ x
 // shard table (peer-mapped pointers).  Remote rows travel over NVLink as 128-bit loads issued by
 // the consuming kernel itself - the halo exchange IS the gather.
 // ------------------------------------------------------------------------------------------
-struct ShardTab {
-  const float* base[GS_MAX_SHARDS];
-  int32_t n_shards, my_shard;
-  int64_t rows_per_shard, n_global_rows;
-};
-
-__device__ __forceinline__ const float* shard_row(const ShardTab& t, int64_t id, int64_t pitch) {
-  if (id < 0 || id >= t.n_global_rows - 1) return t.base[t.my_shard] + t.rows_per_shard * pitch;  // local zero row
-  int64_t o = id / t.rows_per_shard;
-  return t.base[o] + (id - o * t.rows_per_shard) * pitch;
-}
-
 template <int kUnroll>
-__global__ void __launch_bounds__(256) gather_mean_sharded_kernel(const __grid_constant__ ShardTab st, int F, int64_t pitch,
+__global__ void __launch_bounds__(256) gather_mean_sharded_kernel(const __grid_constant__ ShardRows st, int F,
                                                                   const __grid_constant__ SegTable tab, int include_self,
                                                                   float* __restrict__ out_self,
                                                                   float* __restrict__ out_mean, int64_t out_pitch) {
@@ -411,7 +483,7 @@ __global__ void __launch_bounds__(256) gather_mean_sharded_kernel(const __grid_c
     const gs_segment& sg = tab.s[find_segment(tab, r, i)];
     const int k = sg.k;
     const int64_t orow = sg.out_row0 + i;
-    const float* srow = shard_row(st, sg.self_ids ? (int64_t)sg.self_ids[i] : sg.self_row0 + i, pitch);
+    const float* srow = st.row(sg.self_ids ? (int64_t)sg.self_ids[i] : sg.self_row0 + i);
     for (int c = threadIdx.x; c < ncol4; c += blockDim.x) {
       const int col0 = c * 4;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -422,7 +494,7 @@ __global__ void __launch_bounds__(256) gather_mean_sharded_kernel(const __grid_c
           float4 v[kUnroll];
 #pragma unroll
           for (int u = 0; u < kUnroll; ++u) {
-            const float* p = shard_row(st, sg.neigh_ids ? (int64_t)sg.neigh_ids[i * k + j + u] : sg.neigh_row0 + i * k + j + u, pitch);
+            const float* p = st.row(sg.neigh_ids ? (int64_t)sg.neigh_ids[i * k + j + u] : sg.neigh_row0 + i * k + j + u);
             v[u] = ldg_nc_f4(reinterpret_cast<const float4*>(p) + c);
           }
 #pragma unroll
@@ -431,7 +503,7 @@ __global__ void __launch_bounds__(256) gather_mean_sharded_kernel(const __grid_c
           }
         }
         for (; j < k; ++j) {
-          const float* p = shard_row(st, sg.neigh_ids ? (int64_t)sg.neigh_ids[i * k + j] : sg.neigh_row0 + i * k + j, pitch);
+          const float* p = st.row(sg.neigh_ids ? (int64_t)sg.neigh_ids[i * k + j] : sg.neigh_row0 + i * k + j);
           float4 v = ldg_nc_f4(reinterpret_cast<const float4*>(p) + c);
           acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
@@ -449,7 +521,7 @@ __global__ void __launch_bounds__(256) gather_mean_sharded_kernel(const __grid_c
 }
 
 // one warp per row, 128-bit loads through the shard table
-__global__ void __launch_bounds__(256) gather_rows_sharded_kernel(const __grid_constant__ ShardTab st, int F, int64_t pitch,
+__global__ void __launch_bounds__(256) gather_rows_sharded_kernel(const __grid_constant__ ShardRows st, int F,
                                                                   const int32_t* __restrict__ ids, int64_t n,
                                                                   float* __restrict__ out, int64_t out_pitch) {
   const int lane = threadIdx.x & 31;
@@ -457,7 +529,7 @@ __global__ void __launch_bounds__(256) gather_rows_sharded_kernel(const __grid_c
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int ncol4 = (int)(out_pitch >> 2);
   for (int64_t i = warp; i < n; i += nwarps) {
-    const float* p = shard_row(st, ids[i], pitch);
+    const float* p = st.row(ids[i]);
     for (int c = lane; c < ncol4; c += 32) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c * 4 < F) v = mask_tail(ldg_nc_f4(reinterpret_cast<const float4*>(p) + c), c * 4, F);
@@ -551,7 +623,7 @@ int32_t gs_gather_mean(const void* src, int32_t dtype, int64_t n_src_rows, int32
   const int variant = gs::tuning("gather_variant", 2);   // 2: grouped double-buffered TMA (default), 1: whole-node TMA, 0: LDG
   if (variant == 2 && ncol4 <= 2 * 160) {
     {
-      const int32_t rc_attr = gs::ensure_dyn_smem((const void*)gs::gather_mean_tma2_kernel, 200 * 1024);
+      const int32_t rc_attr = gs::ensure_dyn_smem((const void*)gs::gather_mean_tma2_kernel<gs::DenseRows>, 200 * 1024);
       if (rc_attr != GS_OK) return rc_attr;
     }
     const size_t smem2 = (size_t)2 * gs::kGroupRows * row_bytes;
@@ -565,9 +637,9 @@ int32_t gs_gather_mean(const void* src, int32_t dtype, int64_t n_src_rows, int32
     int64_t blocks = tab.total_rows;
     int64_t cap = (int64_t)gs::sm_count() * per_sm;
     if (blocks > cap) blocks = cap;
-    gs::gather_mean_tma2_kernel<<<(unsigned)blocks, threads, smem2, st>>>(fsrc, n_src_rows, F, pitch, tab, include_self,
-                                                                          (float*)out_self, (float*)out_mean, out_pitch,
-                                                                          row_bytes);
+    const gs::DenseRows rows_of{fsrc, n_src_rows, pitch};
+    gs::gather_mean_tma2_kernel<gs::DenseRows><<<(unsigned)blocks, threads, smem2, st>>>(
+        rows_of, F, tab, include_self, (float*)out_self, (float*)out_mean, out_pitch, row_bytes);
     return gs::launch_check("gather_mean_tma2_kernel");
   }
   if (variant >= 1 && smem <= 200 * 1024) {
@@ -600,6 +672,37 @@ int32_t gs_gather_mean(const void* src, int32_t dtype, int64_t n_src_rows, int32
   return gs::launch_check("gather_mean_ldg_kernel");
 }
 
+int32_t gs_gather_rows_f32(const void* feats, int32_t dtype, int64_t n_rows, int32_t F, int64_t pitch, const int32_t* ids,
+                           int64_t row0, int64_t n, float* out, int64_t out_pitch, void* stream) {
+  GS_REQUIRE(n >= 0 && F >= 0, "gs_gather_rows_f32: negative size");
+  if (n == 0 || out_pitch == 0) return GS_OK;
+  GS_REQUIRE(feats && out, "gs_gather_rows_f32: NULL pointer");
+  GS_REQUIRE(dtype == GS_F32 || dtype == GS_BF16, "gs_gather_rows_f32: dtype %d", dtype);
+  GS_REQUIRE(n_rows > 0 && pitch >= F && out_pitch >= F, "gs_gather_rows_f32: pitch < F");
+  int64_t blocks = (n + 7) / 8;
+  int64_t cap = (int64_t)gs::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (dtype == GS_F32)
+    gs::gather_rows_to_f32_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const float*)feats, n_rows, F, pitch, ids, row0, n, out, out_pitch);
+  else
+    gs::gather_rows_to_f32_kernel<uint16_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const uint16_t*)feats, n_rows, F, pitch, ids, row0, n, out, out_pitch);
+  return gs::launch_check("gather_rows_to_f32_kernel");
+}
+
+int32_t gs_cast_rows_bf16(const float* x, int64_t n, int32_t F, int64_t ldx, void* out_bf16, int64_t out_pitch,
+                          void* stream) {
+  GS_REQUIRE(n >= 0 && F >= 0 && ldx >= F && out_pitch >= F, "gs_cast_rows_bf16: bad sizes");
+  if (n == 0 || out_pitch == 0) return GS_OK;
+  GS_REQUIRE(x && out_bf16, "gs_cast_rows_bf16: NULL pointer");
+  int64_t blocks = (n * out_pitch + 255) / 256;
+  int64_t cap = (int64_t)gs::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  gs::cast_rows_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, F, ldx, (uint16_t*)out_bf16, out_pitch);
+  return gs::launch_check("cast_rows_bf16_kernel");
+}
+
 int32_t gs_segment_max(const float* x, int64_t n, int32_t k, int32_t C, int64_t ldx, float* out, int64_t ldo,
                        void* stream) {
   GS_REQUIRE(n >= 0 && k >= 1 && C >= 0, "gs_segment_max: bad sizes");
@@ -628,23 +731,30 @@ int32_t gs_l2_normalize_rows(float* x, int64_t n, int32_t C, int64_t ldx, void* 
 // ---------------------------------------------------------------------------------------------
 // node-partitioned table entry points
 // ---------------------------------------------------------------------------------------------
-static int32_t fill_shard_tab(const gs_sharded_table* t, gs::ShardTab& st, int64_t pitch, const char* who) {
+static int32_t fill_shard_tab(const gs_sharded_table* t, gs::ShardRows& sr, int64_t pitch, const char* who) {
   GS_REQUIRE(t != nullptr, "%s: table is NULL", who);
   GS_REQUIRE(t->n_shards >= 1 && t->n_shards <= GS_MAX_SHARDS, "%s: n_shards=%d (max %d)", who, t->n_shards, GS_MAX_SHARDS);
   GS_REQUIRE(t->my_shard >= 0 && t->my_shard < t->n_shards, "%s: my_shard=%d", who, t->my_shard);
-  GS_REQUIRE(t->rows_per_shard > 0 && t->n_global_rows > 0 &&
-                 t->rows_per_shard * t->n_shards >= t->n_global_rows - 1,
-             "%s: rows_per_shard * n_shards must cover n_global_rows - 1", who);
+  GS_REQUIRE(t->n_global_rows > 0 && t->row_start[0] == 0 && t->row_start[t->n_shards] == t->n_global_rows - 1,
+             "%s: row_start must run from 0 to n_global_rows - 1", who);
+  for (int i = 0; i < t->n_shards; ++i)
+    GS_REQUIRE(t->row_start[i] <= t->row_start[i + 1], "%s: row_start must be non-decreasing (shard %d)", who, i);
+  GS_REQUIRE(t->zero_row >= 0, "%s: zero_row < 0", who);
   GS_REQUIRE(pitch % 4 == 0, "%s: pitch must be a multiple of 4 floats", who);
-  memset(&st, 0, sizeof(st));
+  memset(&sr, 0, sizeof(sr));
+  gs::ShardTab& st = sr.t;
   for (int i = 0; i < t->n_shards; ++i) {
     GS_REQUIRE(t->base[i] != nullptr && gs::aligned16(t->base[i]), "%s: shard %d pointer NULL or not 16-byte aligned", who, i);
     st.base[i] = (const float*)t->base[i];
   }
+  for (int i = 0; i <= t->n_shards; ++i) st.row_start[i] = t->row_start[i];
+  for (int i = t->n_shards + 1; i <= GS_MAX_SHARDS; ++i) st.row_start[i] = t->row_start[t->n_shards];
   st.n_shards = t->n_shards;
   st.my_shard = t->my_shard;
-  st.rows_per_shard = t->rows_per_shard;
   st.n_global_rows = t->n_global_rows;
+  st.zero_row = t->zero_row;
+  st.remap = t->remap;
+  sr.pitch = pitch;
   return GS_OK;
 }
 
@@ -656,8 +766,8 @@ int32_t gs_gather_mean_sharded(const gs_sharded_table* table_host, int32_t dtype
   GS_REQUIRE(dtype == GS_F32, "gs_gather_mean_sharded: only GS_F32 (dtype=%d)", dtype);
   GS_REQUIRE(n_segments >= 0 && n_segments <= GS_MAX_SEGMENTS && (segments_host || n_segments == 0),
              "gs_gather_mean_sharded: bad segments");
-  gs::ShardTab st;
-  int32_t rc = fill_shard_tab(table_host, st, pitch, "gs_gather_mean_sharded");
+  gs::ShardRows sr;
+  int32_t rc = fill_shard_tab(table_host, sr, pitch, "gs_gather_mean_sharded");
   if (rc != GS_OK) return rc;
   gs::SegTable tab;
   memset(&tab, 0, sizeof(tab));
@@ -673,21 +783,40 @@ int32_t gs_gather_mean_sharded(const gs_sharded_table* table_host, int32_t dtype
                  F > 0 && pitch >= ((F + 3) / 4) * 4 && out_pitch >= F,
              "gs_gather_mean_sharded: bad output / pitch");
   const int ncol4 = (int)(out_pitch / 4);
+  const int row_bytes = ((F + 3) / 4) * 16;
+  // default: the grouped double-buffered bulk-copy kernel of the dense table with peer-mapped row addresses - a
+  // remote row is one cp.async.bulk over NVLink straight into this SM's shared memory (gather_variant=0: 128-bit loads)
+  if (gs::tuning("gather_variant", 2) != 0 && ncol4 <= 2 * 160) {
+    const int32_t rc_attr = gs::ensure_dyn_smem((const void*)gs::gather_mean_tma2_kernel<gs::ShardRows>, 200 * 1024);
+    if (rc_attr != GS_OK) return rc_attr;
+    const size_t smem2 = (size_t)2 * gs::kGroupRows * row_bytes;
+    int threads = ((ncol4 + 31) / 32) * 32;
+    if (threads > 160) threads = 160;
+    if (threads < 32) threads = 32;
+    int per_sm = (int)((224 * 1024) / (smem2 + 1024));
+    if (per_sm < 1) per_sm = 1;
+    int64_t blocks = tab.total_rows;
+    int64_t cap = (int64_t)gs::sm_count() * per_sm;
+    if (blocks > cap) blocks = cap;
+    gs::gather_mean_tma2_kernel<gs::ShardRows><<<(unsigned)blocks, threads, smem2, (cudaStream_t)stream>>>(
+        sr, F, tab, include_self, (float*)out_self, (float*)out_mean, out_pitch, row_bytes);
+    return gs::launch_check("gather_mean_tma2_kernel<ShardRows>");
+  }
   int threads = ((ncol4 + 31) / 32) * 32;
   if (threads > 256) threads = 256;
   int64_t blocks = tab.total_rows;
   int64_t cap = (int64_t)gs::sm_count() * gs::tuning("gather_ctas_per_sm", 8);
   if (blocks > cap) blocks = cap;
   gs::gather_mean_sharded_kernel<5><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-      st, F, pitch, tab, include_self, (float*)out_self, (float*)out_mean, out_pitch);
+      sr, F, tab, include_self, (float*)out_self, (float*)out_mean, out_pitch);
   return gs::launch_check("gather_mean_sharded_kernel");
 }
 
 int32_t gs_gather_rows_sharded(const gs_sharded_table* table_host, int32_t dtype, int32_t F, int64_t pitch,
                                const int32_t* ids, int64_t n, void* out, int64_t out_pitch, void* stream) {
   GS_REQUIRE(dtype == GS_F32, "gs_gather_rows_sharded: only GS_F32 (dtype=%d)", dtype);
-  gs::ShardTab st;
-  int32_t rc = fill_shard_tab(table_host, st, pitch, "gs_gather_rows_sharded");
+  gs::ShardRows sr;
+  int32_t rc = fill_shard_tab(table_host, sr, pitch, "gs_gather_rows_sharded");
   if (rc != GS_OK) return rc;
   if (n == 0) return GS_OK;
   GS_REQUIRE(ids && out && gs::aligned16(out) && out_pitch % 4 == 0 && F > 0 && pitch >= ((F + 3) / 4) * 4 && out_pitch >= F,
@@ -695,8 +824,7 @@ int32_t gs_gather_rows_sharded(const gs_sharded_table* table_host, int32_t dtype
   int64_t blocks = (n + 7) / 8;
   int64_t cap = (int64_t)gs::sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  gs::gather_rows_sharded_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(st, F, pitch, ids, n, (float*)out,
-                                                                                      out_pitch);
+  gs::gather_rows_sharded_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(sr, F, ids, n, (float*)out, out_pitch);
   return gs::launch_check("gather_rows_sharded_kernel");
 }
 

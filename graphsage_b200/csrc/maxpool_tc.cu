@@ -262,7 +262,10 @@ __device__ __forceinline__ void mp_epilogue_role(const MpParams& prm, int et, in
 
 // MP_SA A stages of 8 KB, MP_INFLIGHT cp.async K-blocks in flight per producer thread: <7, 5> when the resident
 // weights need <= 19 slots (K <= 608), else <6, 4>
-template <int MP_SA, int MP_INFLIGHT>
+// kAsyncArrive: the producers never wait for their own copies - each thread hands the stage's full barrier a
+// cp.async.mbarrier.arrive.noinc, which the hardware fires when that thread's copies have landed (no cp.async group
+// wait, no proxy fence, no elected arrive; the barrier counts one arrival per producer THREAD).
+template <int MP_SA, int MP_INFLIGHT, bool kAsyncArrive = false>
 __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid_constant__ MpParams prm) {
   static_assert(MP_INFLIGHT + 2 <= MP_SA, "a stage must be free while MP_INFLIGHT copies fly and one is consumed");
   extern __shared__ unsigned char smem_raw[];
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < MP_SA; ++s) {
-      mbar_init(&full_a[s], MP_PROD_WARPS);   // one arrive per producer warp
+      mbar_init(&full_a[s], kAsyncArrive ? MP_PROD_WARPS * 32 : MP_PROD_WARPS);   // one arrive per producer thread / warp
       mbar_init(&empty_a[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -339,6 +342,10 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
           if (rowp[i] != nullptr && col < prm.K) nbytes = min(8, prm.K - col) * 2;
           const void* src = nbytes ? (const void*)(rowp[i] + col) : (const void*)prm.table;
           cp_async16(a_img + sw64_off(r0 + 32 * i, c), src, nbytes);
+        }
+        if constexpr (kAsyncArrive) {
+          cp_async_mbar_arrive_noinc(&full_a[s]);
+          continue;
         }
         cp_async_commit();
         ++pending;
@@ -780,6 +787,16 @@ static int32_t pool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K,
     else
       gs::maxpool_mlp_g4_kernel<6><<<(unsigned)ctas, (6 + 6) * 32, gs::MP_SMEM, (cudaStream_t)stream>>>(prm, tmap);
     return gs::launch_check("maxpool_mlp_g4_kernel");
+  }
+  if (producer == -1) {       // cp.async producers with hardware-fired arrives (no group wait / proxy fence)
+    int32_t rc_attr = gs::ensure_dyn_smem((const void*)gs::maxpool_mlp_kernel<7, 5, true>, gs::MP_SMEM);
+    if (rc_attr == GS_OK) rc_attr = gs::ensure_dyn_smem((const void*)gs::maxpool_mlp_kernel<6, 4, true>, gs::MP_SMEM);
+    if (rc_attr != GS_OK) return rc_attr;
+    if (prm.kblocks <= gs::MP_RING - 7)
+      gs::maxpool_mlp_kernel<7, 5, true><<<(unsigned)ctas, gs::MP_THREADS, gs::MP_SMEM, (cudaStream_t)stream>>>(prm);
+    else
+      gs::maxpool_mlp_kernel<6, 4, true><<<(unsigned)ctas, gs::MP_THREADS, gs::MP_SMEM, (cudaStream_t)stream>>>(prm);
+    return gs::launch_check("maxpool_mlp_kernel<async arrive>");
   }
   if (prm.kblocks <= gs::MP_RING - 7)
     gs::maxpool_mlp_kernel<7, 5><<<(unsigned)ctas, gs::MP_THREADS, gs::MP_SMEM, (cudaStream_t)stream>>>(prm);

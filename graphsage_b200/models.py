@@ -148,7 +148,8 @@ class SampleAndAggregate(object):
                 else:
                     segs.append(ops.Seg(counts[hop], k, self_row0=row0[hop], neigh_row0=row0[hop + 1],
                                         out_row0=row0[hop]))
-            src = aggregators[layer].aggregate_rows(src, segs, final=_final if layer == L - 1 else None)
+            src = aggregators[layer].aggregate_rows(src, segs, final=_final if layer == L - 1 else None,
+                                                    src_persistent=(layer == 0))
         return src[:counts[0]], aggregators
 
     def _aggregate_materialised(self, samples, feats, dims, num_samples, support_sizes, batch_size, aggregators,
@@ -353,8 +354,13 @@ class PipelinedForward(object):
         r = self.step % self.depth
         run = self.runners[r]
         hs = self._fast_handles() if self.use_c_step else None
+        if ids_host.numel() != run.ids.numel():
+            raise ValueError("PipelinedForward.submit: %d ids for a runner captured at batch size %d (pad the last "
+                             "batch or build another runner)" % (ids_host.numel(), run.ids.numel()))
+        if out_host.numel() != run.out.numel() or out_host.dtype != torch.float32:
+            raise ValueError("PipelinedForward.submit: out_host must be float32 with %d elements" % run.out.numel())
         if hs and ids_host.dtype == torch.int32 and not ids_host.is_cuda and ids_host.is_contiguous() \
-                and out_host.is_contiguous() and out_host.numel() * 4 == hs[r][5]:
+                and not out_host.is_cuda and out_host.is_contiguous():
             execs, n, ids_dev, ids_bytes, out_dev, out_bytes, ev_ids, ev_done, ev_drained = hs[r]
             ops.check(ops.lib().gs_pipeline_step(ids_host.data_ptr(), ids_dev, ids_bytes, execs, n, out_dev,
                                                  out_host.data_ptr(), out_bytes, self.h2d.cuda_stream,

@@ -160,6 +160,43 @@ def gather_rows(feats, ids, out=None):
     return out
 
 
+def gather_rows_f32(feats, ids=None, row0=0, n=None, out=None):
+    """embedding_lookup widened to fp32 (reference graphsage/models.py:299): rows ids[i] (or row0 + i) of a bf16 / fp32
+    table into an fp32 [n, pad_cols(F)] buffer (returned as its [:, :F] view); pad columns are zeroed."""
+    require_cuda(feats, ids, out)
+    if feats.dim() != 2 or feats.stride(1) != 1:
+        raise ValueError("features must be a row-major 2-D tensor")
+    F = feats.shape[1]
+    if ids is not None:
+        ids = _i32(ids.reshape(-1), "ids")
+        n = ids.numel() if n is None else int(n)
+    if n is None:
+        raise ValueError("n is required without ids")
+    if out is None:
+        out = torch.empty((n, pad_cols(F)), dtype=torch.float32, device=feats.device)[:, :F]
+    if out.dtype != torch.float32 or out.stride(1) != 1 or out.shape[0] < n:
+        raise ValueError("out must be a row-major float32 matrix with >= n rows")
+    check(lib().gs_gather_rows_f32(ptr(feats), _dtype_code(feats), feats.shape[0], F, feats.stride(0), ptr(ids), int(row0), n,
+                                   ptr(out), out.stride(0), stream_ptr()))
+    _launched(1 if n else 0)
+    return out
+
+
+def cast_rows_bf16(x, out=None):
+    """fp32 [n, F] -> bf16 [n, pad_cols(F)] (round to nearest even, pad columns zeroed); returns the [:, :F] view."""
+    require_cuda(x, out)
+    if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("x must be a row-major float32 matrix")
+    n, F = x.shape
+    if out is None:
+        out = torch.empty((n, pad_cols(F)), dtype=torch.bfloat16, device=x.device)[:, :F]
+    if out.dtype != torch.bfloat16 or out.stride(1) != 1 or out.shape[0] < n or out.stride(0) < F:
+        raise ValueError("out must be a row-major bfloat16 matrix with >= n rows")
+    check(lib().gs_cast_rows_bf16(ptr(x), n, F, x.stride(0), ptr(out), out.stride(0), stream_ptr()))
+    _launched(1 if n else 0)
+    return out
+
+
 class Seg(object):
     """One hop's rows for gather_mean: n output rows with fanout k.  Neighbour j of row i is
     src[neigh_ids[i*k + j]] (or src[neigh_row0 + i*k + j] when neigh_ids is None); the self row is

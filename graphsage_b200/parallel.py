@@ -25,13 +25,66 @@ def rows_per_shard(n_nodes, world):
     return (int(n_nodes) + world - 1) // world
 
 
-def owner_of(ids, n_nodes, world):
-    """Owner rank of each global id (numpy or torch); the dummy id n_nodes maps to -1 (every rank has a zero row)."""
+def uniform_bounds(n_nodes, world):
+    """row_start of the equal-range partition: shard r owns [r*R, min(N, (r+1)*R)), R = ceil(N / world)."""
     R = rows_per_shard(n_nodes, world)
-    o = ids // R
+    return [min(int(n_nodes), r * R) for r in range(world)] + [int(n_nodes)]
+
+
+def community_bounds(comm, world):
+    """row_start aligned with communities: `comm` is the community of every node with communities CONTIGUOUS in id
+    order (synthetic.reddit_like relabels nodes that way); each cut is moved to the nearest community start, so no
+    community straddles two GPUs (locality-aware partition)."""
+    comm = np.asarray(comm)
+    n = len(comm)
+    starts = np.concatenate([[0], np.nonzero(comm[1:] != comm[:-1])[0] + 1, [n]])
+    bounds = [0]
+    for r in range(1, world):
+        c = int(starts[np.argmin(np.abs(starts - r * n / float(world)))])
+        bounds.append(max(c, bounds[-1]))
+    return bounds + [n]
+
+
+def owner_of(ids, n_nodes, world, row_start=None):
+    """Owner rank of each global id (numpy or torch); ids outside [0, n_nodes) - the dummy id included - map to -1
+    (every rank has a zero row)."""
+    rs = uniform_bounds(n_nodes, world) if row_start is None else list(row_start)
     if torch.is_tensor(ids):
+        b = torch.as_tensor(rs[1:-1], dtype=ids.dtype, device=ids.device)
+        o = torch.bucketize(ids, b, right=True)
         return torch.where((ids < 0) | (ids >= n_nodes), torch.full_like(o, -1), o)
+    o = np.searchsorted(np.asarray(rs[1:-1]), ids, side="right")
     return np.where((ids < 0) | (ids >= n_nodes), -1, o)
+
+
+def default_cache_rows(n_nodes, world):
+    """Replica budget used by bench.py when none is given: as many rows as one shard (each GPU then stores 2/world
+    of the table)."""
+    return rows_per_shard(n_nodes, world) if world > 1 else 0
+
+
+def hot_remote_rows(adj, n_nodes, world, rank, n_rows, row_start=None):
+    """The `n_rows` REMOTE nodes this rank's batches will read most, by the access probabilities the padded table
+    implies for seeds owned by `rank` (owner-computes): hop-1 nodes are the entries of the own rows' adjacency rows,
+    hop-2 nodes the entries of THEIR rows; a node's score is its expected number of reads per seed (hop 1 + hop 2,
+    fanout-weighted 10 and 250).  Returns sorted int64 ids (possibly fewer than n_rows)."""
+    if n_rows <= 0 or world <= 1:
+        return np.zeros(0, dtype=np.int64)
+    adj = np.asarray(adj)
+    md = adj.shape[1]
+    rs = uniform_bounds(n_nodes, world) if row_start is None else list(row_start)
+    lo, hi = rs[rank], rs[rank + 1]
+    p1 = np.bincount(adj[lo:hi].reshape(-1), minlength=n_nodes + 1).astype(np.float64)
+    p1 /= max(p1.sum(), 1.0)                                  # P(a hop-1 draw lands on u)
+    nz = np.nonzero(p1[:n_nodes])[0]
+    p2 = np.bincount(adj[nz].reshape(-1), weights=np.repeat(p1[nz] / md, md), minlength=n_nodes + 1)
+    score = (10.0 * p1 + 250.0 * p2)[:n_nodes]
+    score[lo:hi] = -1.0                                       # own rows need no replica
+    n_rows = int(min(n_rows, int((score > 0).sum())))
+    if n_rows == 0:
+        return np.zeros(0, dtype=np.int64)
+    hot = np.argpartition(-score, n_rows - 1)[:n_rows]
+    return np.sort(hot).astype(np.int64)
 
 
 def locality_order(comm):
@@ -53,13 +106,13 @@ def relabel_graph(indptr, indices, order, inv):
     return new_ptr, inv[np.asarray(indices)[ent]].astype(np.int32)
 
 
-def route_seeds(seeds, n_nodes, group=None):
+def route_seeds(seeds, n_nodes, group=None, row_start=None):
     """Owner-computes routing: every rank passes the seeds it was handed; returns the seeds this rank owns
     (all_to_all of variable-length id lists; works on gloo and nccl)."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
     seeds = seeds.reshape(-1)
-    own = owner_of(seeds, n_nodes, world).clamp(min=0)
+    own = owner_of(seeds, n_nodes, world, row_start).clamp(min=0)
     order = torch.argsort(own, stable=True)
     send = seeds[order].contiguous()
     counts = torch.bincount(own, minlength=world)
@@ -82,34 +135,60 @@ class _CudaView(object):
 class ShardedFeatures(object):
     """This rank's shard of a node-partitioned [N+1, F] fp32 feature table plus peer mappings of all others.
 
-    local_rows: float32 [n_local, F] rows of global nodes [rank*R, rank*R + n_local) (numpy or tensor).
-    The shard buffer is [R + 1, pitch] with a zero row at index R (the dummy row, reference
-    supervised_train.py:133-135, kept local on every rank).
+    local_rows : float32 [n_local, F] rows of the global nodes [row_start[rank], row_start[rank+1]) (numpy or tensor).
+    row_start  : partition bounds (len world + 1); default = equal ranges (uniform_bounds).
+    replica_ids / replica_rows : optional remote node ids (sorted, unique, none owned by this rank) and their feature
+        rows [len(replica_ids), F]: kept in this rank's own buffer and served locally (hot-row replication, SURVEY 8e iii).
+    The local buffer is [n_local + 1 + n_replicas, pitch]: own rows, the zero row (the dummy row, reference
+    supervised_train.py:133-135, local on every rank), then the replicas.
     """
 
-    def __init__(self, local_rows, n_nodes, group=None, device=None):
+    def __init__(self, local_rows, n_nodes, group=None, device=None, row_start=None, replica_ids=None, replica_rows=None):
         import torch.distributed as dist
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.n_nodes = int(n_nodes)
-        self.R = rows_per_shard(n_nodes, self.world)
+        self.row_start = [int(x) for x in (uniform_bounds(n_nodes, self.world) if row_start is None else row_start)]
+        if len(self.row_start) != self.world + 1 or self.row_start[0] != 0 or self.row_start[-1] != self.n_nodes:
+            raise ValueError("row_start must have world + 1 entries running from 0 to n_nodes")
+        if self.world > _lib.MAX_SHARDS:
+            raise ValueError("at most %d shards" % _lib.MAX_SHARDS)
         local_rows = torch.as_tensor(local_rows, dtype=torch.float32)
         F = local_rows.shape[1]
-        lo = self.rank * self.R
-        n_local = max(0, min(self.R, self.n_nodes - lo))
+        lo, hi = self.row_start[self.rank], self.row_start[self.rank + 1]
+        n_local = hi - lo
+        self.lo, self.hi, self.n_local = lo, hi, n_local
         if local_rows.shape[0] != n_local:
             raise ValueError("rank %d must pass %d rows (got %d)" % (self.rank, n_local, local_rows.shape[0]))
+        rep_ids = np.zeros(0, np.int64) if replica_ids is None else np.asarray(replica_ids, dtype=np.int64).reshape(-1)
+        if len(rep_ids):
+            if replica_rows is None or len(replica_rows) != len(rep_ids):
+                raise ValueError("replica_rows must hold one row per replica id")
+            if (np.diff(rep_ids) <= 0).any() or rep_ids[0] < 0 or rep_ids[-1] >= self.n_nodes \
+                    or ((rep_ids >= lo) & (rep_ids < hi)).any():
+                raise ValueError("replica_ids must be sorted, unique, in range and not owned by this rank")
+        self.replica_ids = rep_ids
         self.shape = (self.n_nodes + 1, F)
         self.pitch = pad_cols(F)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        nbytes = (self.R + 1) * self.pitch * 4
+        rows_total = n_local + 1 + len(rep_ids)
+        nbytes = rows_total * self.pitch * 4
         p = ctypes.c_void_p()
         check(lib().gs_shard_alloc(nbytes, ctypes.byref(p)))
         self._own_ptr = p.value
-        self.local = torch.as_tensor(_CudaView(p.value, (self.R + 1, self.pitch)), device=self.device)
+        self.local = torch.as_tensor(_CudaView(p.value, (rows_total, self.pitch)), device=self.device)
         self.local.zero_()
         self.local[:n_local, :F] = local_rows.to(self.device)
+        self.zero_row = n_local
+        self.remap = None
+        if len(rep_ids):
+            self.local[n_local + 1:, :F] = torch.as_tensor(replica_rows, dtype=torch.float32).to(self.device)
+            remap = np.full(self.n_nodes + 1, -1, dtype=np.int32)
+            remap[lo:hi] = np.arange(n_local, dtype=np.int32)
+            remap[self.n_nodes] = n_local
+            remap[rep_ids] = n_local + 1 + np.arange(len(rep_ids), dtype=np.int32)
+            self.remap = torch.from_numpy(remap).to(self.device)
         torch.cuda.synchronize()
         # exchange IPC handles
         handle = ctypes.create_string_buffer(64)
@@ -129,20 +208,29 @@ class ShardedFeatures(object):
                 check(lib().gs_ipc_import(handles[r], ctypes.byref(q)))
                 self._peer_ptrs.append(q.value)
                 self._table.base[r] = q.value
+        for r in range(self.world + 1):
+            self._table.row_start[r] = self.row_start[r]
         self._table.n_shards = self.world
         self._table.my_shard = self.rank
-        self._table.rows_per_shard = self.R
         self._table.n_global_rows = self.n_nodes + 1
+        self._table.zero_row = self.zero_row
+        self._table.remap = 0 if self.remap is None else self.remap.data_ptr()
         if self.world > 1:
             dist.barrier(group=group)
 
     def c_table(self):
         return ctypes.byref(self._table)
 
-    def remote_fraction(self, ids):
-        """Fraction of the given global ids whose feature row lives on another rank."""
-        own = owner_of(ids.reshape(-1), self.n_nodes, self.world)
-        return float(((own >= 0) & (own != self.rank)).float().mean().item())
+    def remote_fraction(self, ids, use_replicas=True):
+        """Fraction of the given global ids whose feature row must come over NVLink (not owned; with use_replicas,
+        not replicated here either)."""
+        ids = ids.reshape(-1)
+        own = owner_of(ids, self.n_nodes, self.world, self.row_start)
+        remote = (own >= 0) & (own != self.rank)
+        if use_replicas and self.remap is not None:
+            safe = ids.clamp(0, self.n_nodes).long()
+            remote = remote & (self.remap.to(ids.device)[safe] < 0)
+        return float(remote.float().mean().item())
 
     def close(self):
         import torch.distributed as dist

@@ -207,6 +207,11 @@ def differentiable_outputs(model, batch, normalize=True):
 
 def build_aggregators(model):
     """One aggregator per layer, as SampleAndAggregate.aggregate creates them (reference models.py:303-315)."""
+    if float(model.placeholders.get("dropout", 0.) or 0.) != 0.:
+        # the reference applies dropout inside the aggregators and in the prediction Dense (supervised_models.py:88-90);
+        # the differentiable path here has no dropout, so refuse rather than silently train a different model
+        raise NotImplementedError("training with placeholders['dropout'] > 0 is not implemented (forward-only "
+                                  "dropout runs through SampleAndAggregate.aggregate's materialised path)")
     L = len(model.layer_infos)
     aggs = []
     for layer in range(L):

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 1
+#define GS_ABI_VERSION 2
 
 typedef enum {
   GS_OK = 0,
@@ -158,21 +158,27 @@ int32_t gs_gather_mean(const void* src, int32_t dtype, int64_t n_src_rows, int32
 
 /* ---------------------------------------------------------------------------------------------
  * Node-partitioned feature table (multi-GPU; no reference counterpart - the reference is
- * single-device).  Rank r owns global rows [r*rows_per_shard, (r+1)*rows_per_shard); every rank maps all
- * shards into its address space (CUDA IPC over NVLink/NVSwitch), so the gather kernel resolves
- *   row(id) = base[id / rows_per_shard] + (id % rows_per_shard) * pitch
- * and pulls remote rows with plain 128-bit loads: the halo exchange is fused into the gather, no
- * staging buffer, no collective on the data path.  Ids outside [0, n_global_rows-1) - including the
- * dummy id N - read the caller's local zero row (index rows_per_shard of its own shard).
+ * single-device).  Shard r owns the global ids [row_start[r], row_start[r+1]) (contiguous ranges - align them
+ * with communities); every rank maps all shards into its address space (CUDA IPC over NVLink/NVSwitch), so the
+ * gather kernel resolves
+ *   row(id) = base[owner(id)] + (id - row_start[owner(id)]) * pitch
+ * and pulls remote rows itself - one cp.async.bulk per row over NVLink into shared memory (or 128-bit loads with
+ * gather_variant=0): the halo exchange is fused into the gather, no staging buffer, no collective on the data path.
+ * A rank may also hold REPLICAS of the remote rows it reads most: remap (device int32 [n_global_rows], may be NULL)
+ * gives, for every id, the row index inside this rank's OWN buffer (own rows, zero row, replicas) or -1 when the
+ * row has to come from its owner.  Ids outside [0, n_global_rows-1) - including the dummy id N - read the caller's
+ * local zero row (index zero_row of its own buffer).
  * gs_gather_mean_sharded has the semantics of gs_gather_mean with `src` replaced by the table.
  * --------------------------------------------------------------------------------------------- */
 #define GS_MAX_SHARDS 16
 typedef struct {
-  const void* base[GS_MAX_SHARDS]; /* device pointers, shard r = [rows_per_shard + 1, pitch] */
+  const void* base[GS_MAX_SHARDS];       /* device pointers; shard r holds its own rows first */
+  int64_t row_start[GS_MAX_SHARDS + 1];  /* row_start[0] = 0 ... row_start[n_shards] = N */
   int32_t n_shards;
   int32_t my_shard;
-  int64_t rows_per_shard;
-  int64_t n_global_rows;           /* N + 1 (the dummy row is virtual: every shard carries its own zero row) */
+  int64_t n_global_rows;                 /* N + 1 (the dummy row is virtual: every shard carries its own zero row) */
+  int64_t zero_row;                      /* index of the all-zero row inside base[my_shard] */
+  const int32_t* remap;                  /* device, [n_global_rows] or NULL (see above) */
 } gs_sharded_table;
 
 int32_t gs_gather_mean_sharded(const gs_sharded_table* table_host, int32_t dtype, int32_t F, int64_t pitch,
@@ -188,6 +194,17 @@ int32_t gs_shard_free(void* dev_ptr);
 int32_t gs_ipc_export(const void* dev_ptr, uint8_t* handle64_out_host);
 int32_t gs_ipc_import(const uint8_t* handle64_host, void** dev_ptr_out);
 int32_t gs_ipc_close(void* dev_ptr);
+
+/* embedding_lookup (models.py:299) with the result widened to fp32: out[i, 0:F] = (float)feats[ids ? ids[i] : row0 + i, 0:F],
+ * columns F..out_pitch-1 zeroed.  feats is GS_BF16 or GS_F32.  The bf16 max-pool path uses it for the SELF rows, which
+ * meet the fp32 self_weights contraction (aggregators.py:185). */
+int32_t gs_gather_rows_f32(const void* feats, int32_t dtype, int64_t n_rows, int32_t F, int64_t pitch,
+                           const int32_t* ids, int64_t row0, int64_t n, float* out, int64_t out_pitch,
+                           void* stream);
+/* fp32 [n, F] (row stride ldx) -> bf16 [n, out_pitch], round-to-nearest-even, pad columns zeroed: the next layer's
+ * bf16 source table of the max-pool path (the hidden[hop] list of models.py:321-329 kept in the K4 operand type). */
+int32_t gs_cast_rows_bf16(const float* x, int64_t n, int32_t F, int64_t ldx, void* out_bf16, int64_t out_pitch,
+                          void* stream);
 
 /* segmented max over fixed fanout: out[i, c] = max_j x[i*k + j, c]   (aggregators.py:182) */
 int32_t gs_segment_max(const float* x, int64_t n, int32_t k, int32_t C, int64_t ldx,

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(built_lib):
         assert hasattr(lib, name), "symbol %s declared in the header but not exported" % name
     from graphsage_b200 import _lib
     assert set(_lib.exported_symbols()) == declared
-    assert _lib.lib().gs_version() == 1
+    assert _lib.lib().gs_version() == 2
 
 
 def test_perm_prefix_host_matches_oracle(built_lib):

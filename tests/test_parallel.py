@@ -51,6 +51,15 @@ def _cpu_worker(rank, world, port, q):
         assert sorted(sum(got, [])) == sorted(sum(sent, []))
         # dummy / out-of-range ids have no owner
         assert parallel.owner_of(np.array([n_nodes, -1, 0, n_nodes - 1]), n_nodes, world).tolist() == [-1, -1, 0, world - 1]
+        # non-uniform (community-aligned) bounds: numpy and torch agree, routing follows them
+        bounds = [0, 300, n_nodes]
+        ids = np.array([0, 299, 300, 1000, n_nodes, -3])
+        assert parallel.owner_of(ids, n_nodes, world, bounds).tolist() == [0, 0, 1, 1, -1, -1]
+        assert parallel.owner_of(torch.from_numpy(ids), n_nodes, world, bounds).tolist() == [0, 0, 1, 1, -1, -1]
+        mine_b = parallel.route_seeds(seeds, n_nodes, row_start=bounds)
+        assert bool(((mine_b >= bounds[rank]) & (mine_b < bounds[rank + 1])).all())
+        dist.all_gather_object(got, mine_b.tolist())
+        assert sorted(sum(got, [])) == sorted(sum(sent, []))
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
@@ -96,6 +105,40 @@ def test_locality_relabel_preserves_graph():
     assert ((src // R) == (i2 // R)).mean() > 0.6
 
 
+def test_community_bounds_and_hot_rows():
+    from graphsage_b200 import parallel
+    from graphsage_b200.synthetic import reddit_like
+    g = reddit_like(n=6000, f=4, max_degree=16, seed=5, with_features=False)
+    world = 4
+    b = parallel.community_bounds(g["comm"], world)
+    assert b[0] == 0 and b[-1] == 6000 and len(b) == world + 1 and all(x <= y for x, y in zip(b, b[1:]))
+    for cut in b[1:-1]:
+        assert g["comm"][cut] != g["comm"][cut - 1]                 # every cut sits on a community start
+    assert parallel.uniform_bounds(10, 4) == [0, 3, 6, 9, 10] and parallel.uniform_bounds(2, 4) == [0, 1, 2, 2, 2]
+    # aligned cuts cross fewer table entries than equal ranges
+    def cross(bounds):
+        own = parallel.owner_of(np.arange(6000), 6000, world, bounds)
+        ent = g["adj"][:6000]
+        o2 = parallel.owner_of(ent, 6000, world, bounds)
+        return float(((o2 != own[:, None]) & (o2 >= 0)).mean())
+    assert cross(b) <= cross(parallel.uniform_bounds(6000, world)) + 1e-9
+    # hot rows: remote only, sorted unique, and they cover more reads than the same number of arbitrary remote rows
+    rank = 1
+    hot = parallel.hot_remote_rows(g["adj"], 6000, world, rank, 400, row_start=b)
+    assert len(hot) == 400 and (np.diff(hot) > 0).all() and not ((hot >= b[rank]) & (hot < b[rank + 1])).any()
+    import oracle
+    rs = np.random.RandomState(0)
+    seeds = rs.randint(b[rank], b[rank + 1], size=256).astype(np.int32)
+    samples, _ = oracle.sample_khop(g["adj"], seeds, [5, 4], 1, 0)
+    ids = np.concatenate(samples)
+    remote = ids[(parallel.owner_of(ids, 6000, world, b) != rank) & (ids < 6000)]
+    cov_hot = np.isin(remote, hot).mean()
+    others = np.setdiff1d(np.arange(6000), np.arange(b[rank], b[rank + 1]))
+    cov_rand = np.isin(remote, rs.choice(others, size=400, replace=False)).mean()
+    assert cov_hot > cov_rand
+    assert len(parallel.hot_remote_rows(g["adj"], 6000, 1, 0, 100)) == 0
+
+
 def _gpu_worker(rank, world, port, q):
     try:
         _init(rank, world, port, "nccl")
@@ -110,9 +153,11 @@ def _gpu_worker(rank, world, port, q):
         seeds = rs.randint(0, n, size=B).astype(np.int32)
         seeds[0] = 5
         dev = torch.device("cuda", rank)
-        R = parallel.rows_per_shard(n, world)
-        lo, hi = rank * R, min(n, (rank + 1) * R)
-        shard = parallel.ShardedFeatures(feats[lo:hi], n)
+        bounds = [0, 1300, n]                               # deliberately unequal ranges
+        lo, hi = bounds[rank], bounds[rank + 1]
+        hot = parallel.hot_remote_rows(adj, n, world, rank, 200, row_start=bounds)
+        assert len(hot) == 200
+        shard = parallel.ShardedFeatures(feats[lo:hi], n, row_start=bounds, replica_ids=hot, replica_rows=feats[hot])
         adj_dev = torch.from_numpy(adj).to(dev)
         full = torch.from_numpy(np.vstack([feats, np.zeros((1, f), np.float32)])).to(dev)
         outs = {}
@@ -131,8 +176,19 @@ def _gpu_worker(rank, world, port, q):
         ids = torch.from_numpy(rs.randint(0, n + 1, size=5000).astype(np.int32)).to(dev)
         rows = gs.ops.gather_rows(shard, ids)
         assert torch.equal(rows, full[ids.long()])
-        frac = shard.remote_fraction(ids)
-        assert 0.3 < frac < 0.7
+        frac0, frac = shard.remote_fraction(ids, use_replicas=False), shard.remote_fraction(ids)
+        assert 0.3 < frac0 < 0.7 and frac < frac0
+        # both data paths of the partitioned gather (bulk copies over the peer mapping / 128-bit loads) agree bit for bit
+        s0 = torch.from_numpy(rs.randint(0, n, size=64).astype(np.int32)).to(dev)
+        s1 = torch.from_numpy(rs.randint(0, n + 1, size=64 * 25).astype(np.int32)).to(dev)
+        seg = [gs.ops.Seg(64, 25, self_ids=s0, neigh_ids=s1)]
+        a = gs.ops.gather_mean(shard, seg)
+        gs._lib.set_tuning("gather_variant", 0)
+        b = gs.ops.gather_mean(shard, seg)
+        gs._lib.set_tuning("gather_variant", 2)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+        ref_self = full[s0.long()]
+        assert torch.equal(a[0][:, :f], ref_self)
         shard.close()
         q.put((rank, "ok"))
     except Exception:  # pragma: no cover
@@ -172,4 +228,38 @@ def test_sharded_table_single_rank_matches_dense():
     b = gs.ops.gather_mean(full, seg, include_self=True)
     gs._lib.set_tuning("gather_variant", 2)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    shard.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,concat,dim", [("mean", True, 128), ("gcn", False, 256)])
+def test_partitioned_forward_single_rank_vs_oracle(kind, concat, dim):
+    """The node-partitioned path (ShardedFeatures + the sharded gather kernels) against the ORACLE, runnable on a
+    1-GPU box: one shard, same kernels and address arithmetic as with N ranks (reference models.py:254-330)."""
+    import graphsage_b200 as gs
+    import oracle
+    from conftest import rel_err
+    from graphsage_b200 import parallel
+    rs = np.random.RandomState(2)
+    n, md, f, B = 3001, 32, 602, 64
+    adj = rs.randint(0, n, size=(n + 1, md)).astype(np.int32)
+    adj[n] = n
+    adj[7] = n                                             # isolated node: dummy neighbours (zero row)
+    feats = rs.randn(n, f).astype(np.float32)
+    seeds = rs.randint(0, n, size=B).astype(np.int32)
+    seeds[0] = 7
+    shard = parallel.ShardedFeatures(feats, n)
+    adj_dev = torch.from_numpy(adj).cuda()
+    for math in ("fp32", "tf32x3"):
+        gs.set_default_math(math)
+        sampler = gs.UniformNeighborSampler(adj_dev, seed=123)
+        infos = [gs.SAGEInfo("node", sampler, 25, dim), gs.SAGEInfo("node", sampler, 10, dim)]
+        m = gs.SampleAndAggregate({"batch_size": B, "dropout": 0.}, shard, adj_dev, None, infos, concat=concat,
+                                  aggregator_type=kind)
+        out = m.forward(torch.from_numpy(seeds), normalize=True).cpu().numpy()
+        aggs = [dict(type=kind, **{k: v.cpu().numpy() for k, v in a.vars.items()}) for a in m.aggregators]
+        ref = oracle.forward_2hop(adj, np.vstack([feats, np.zeros((1, f), np.float32)]), seeds, [25, 10], aggs, concat,
+                                  123, 0, normalize=True)
+        assert rel_err(out, ref) < 1e-4, (kind, math)
+    gs.set_default_math("fp32")
     shard.close()

@@ -1,9 +1,7 @@
 """GPU: training step with the pooling aggregators - loss and gradients of SupervisedGraphsage
 (aggregator_type maxpool / meanpool, unfused fp32 kernels) against torch-CPU autograd on the oracle's op sequence.
 
-Collected last and marked xfail(strict=False): this path was written after the round's GPU budget was spent (its
-gradient formulas and autograd wiring are covered on CPU by tests/test_pool_training_cpu.py), so its first GPU run must
-not be able to stop the suite; an XPASS here is the expected outcome."""
+First run on a B200 in round 1 (passed); a regression now fails the suite."""
 import numpy as np
 import pytest
 import torch
@@ -11,7 +9,7 @@ import torch
 from conftest import load_golden, rel_err
 from oracle import torch_ref
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU run of the pooling backward")]
+pytestmark = pytest.mark.gpu
 
 
 def _cpu_outputs(adj, feats, seeds, fan, aggs, concat, pool, seed, counter):

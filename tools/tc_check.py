@@ -10,7 +10,7 @@ import numpy as np  # noqa: E402
 import pytest  # noqa: E402
 import torch  # noqa: E402
 
-rc = pytest.main(["tests/test_gpu_parity.py", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider", "-k",
+rc = 0 if os.environ.get("TC_CHECK_SKIP_TESTS", "0") == "1" else pytest.main(["tests/test_gpu_parity.py", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider", "-k",
                   "aggregators_golden or khop_golden or sage_gemm_math or maxpool or meanpool or small_layer or full_size_forward"])
 print("PYTEST_RC", int(rc), flush=True)
 
@@ -66,13 +66,14 @@ if os.environ.get("TC_CHECK_G4", "0") == "1":
         W = torch.randn(KK, HH, device=dev) / 25.0
         b = torch.randn(HH, device=dev) * 0.1
         outs = []
-        for flag in (0, 1, 2):
+        for flag in (0, 1, 2, -1):
             lib.gs_set_tuning(b"k4_producer", flag)
             outs.append(ops.maxpool_mlp_fused(tb[:, :KK], nb, kk, W, b, ops.PackedMlpWeights(), row_ids=rid).clone())
             torch.cuda.synchronize()
-        print("k4_producer 1 / 2 vs 0  groups=%d k=%d K=%d hidden=%d: max |diff| = %.3g / %.3g" % (
-            nb, kk, KK, HH, float((outs[0] - outs[1]).abs().max()), float((outs[0] - outs[2]).abs().max())), flush=True)
-    for flag in (0, 1, 2):
+        print("k4_producer 1 / 2 / -1 vs 0  groups=%d k=%d K=%d hidden=%d: max |diff| = %.3g / %.3g / %.3g" % (
+            nb, kk, KK, HH, float((outs[0] - outs[1]).abs().max()), float((outs[0] - outs[2]).abs().max()),
+            float((outs[0] - outs[3]).abs().max())), flush=True)
+    for flag in (0, 1, 2, -1):
         lib.gs_set_tuning(b"k4_producer", flag)
         t = timeit(lambda: ops.maxpool_mlp_fused(table[:, :F], B * 10, 25, Wm, bm, pk, row_ids=ids), n=20)
         print("k4_producer=%d  K4 maxpool hop2: %.1f us  %.1f TFLOP/s" % (flag, t, 2.0 * B * 250 * F * H / t / 1e6), flush=True)
