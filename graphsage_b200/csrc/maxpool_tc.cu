@@ -50,6 +50,11 @@ struct MpParams {
   float* out;                   // [n_groups, hidden]
   int64_t ldo;
   int32_t issue_elect;          // 1: warp-uniform elect.sync issue (default), 0: one thread inside `if (lane == 0)`
+  int32_t n_stages;             // wide kernel: X stages in the ring
+  int32_t kb_t;                 // tmem kernel: K-blocks of the weight slice held in tensor memory
+  const uint32_t* wrows;        // tmem kernel: Wm^T as rows of bf16 pairs [hidden][kblocks * 32]
+  int32_t dbg;                  // wide kernel timing probes (garbage results): 3 = no producers, MMA warp does not wait for stages;
+                                // 4 = producers run, MMA warp waits and commits but issues no MMA
 };
 
 // byte offset of 16-byte chunk c (0..3) of row r inside a K-major SWIZZLE_64B image (Swizzle<2,4,3>: address bits
@@ -384,6 +389,947 @@ __global__ void __launch_bounds__(MP_THREADS, 1) maxpool_mlp_kernel(const __grid
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// K4, "wide" form (round 2; tuning k4_kernel = 0): the SAME contraction with the operand roles swapped -
+//   D^T[h, r] = sum_c Wm^T[h, c] * X[r, c]      (M = 128 hidden units of this CTA's slice, N = 256 gathered rows, K = 16)
+// i.e. the resident weight slice is the UMMA A operand and the gathered feature rows are the B operand.  Why:
+//   * a fanout group's k rows are now k consecutive accumulator COLUMNS of one TMEM lane, so a thread that reads its
+//     lane with tcgen05.ld (32x32b) holds a whole group in registers: the max (or mean) over the fanout is a register
+//     loop - no shared-memory transpose, no staging tile, no CTA-wide barriers in the epilogue - and lane = hidden
+//     unit makes the result stores coalesced (32 consecutive floats per warp);
+//   * N = 256 per instruction: a tile is 256 gathered rows (10 groups of 25), the weight image is read from shared
+//     memory once per 256 rows instead of once per 128 (96 B/clk of operand reads instead of 128 B/clk at the tensor
+//     pipe's floor), and TMEM holds two 128 x 256 fp32 accumulators (all 512 columns) so the epilogue of tile t
+//     overlaps the MMAs of tile t + 1;
+//   * the gather producers (8 warps, a thread = a 16-byte piece of 4 rows) never wait for their own copies: after
+//     the cp.asyncs of a K-block each thread posts cp.async.mbarrier.arrive.noinc on the stage's full barrier, which the
+//     hardware fires when that thread's copies have landed.  No cp.async group wait, no per-stage proxy fence in the
+//     producers (round 1's limiter: the fence drained every copy the thread still had in flight), no elected arrive.
+//     The generic->async proxy fence is executed once per stage by the MMA warp AFTER it has acquired the barrier.
+// Shared memory: 28 slots of 8 KB = kblocks resident weight images (128 x 64 B, SWIZZLE_64B) + n_stages X stages of two
+// slots (256 x 64 B); K = 608 gives 19 + 4 x 2.
+// ---------------------------------------------------------------------------------------------------------------------
+// Two operand geometries (template): <KC = 32, NT = 256>: 64-byte row pieces (SWIZZLE_64B), 256-row tiles as described
+// above; <KC = 64, NT = 128>: 128-byte row pieces (SWIZZLE_128B; one whole 128-byte line per row per K-block, half as
+// many gather requests per byte), 128-row tiles, K padded to a multiple of 64.
+constexpr int MPW_SMEM_BYTES = 28 * MP_IMG;      // operand ring: resident weight images + X stages
+constexpr int MPW_MAX_STAGES = 8;
+constexpr int MPW_SMEM = MPW_SMEM_BYTES + 1024;
+
+template <int KC>
+__host__ __device__ __forceinline__ uint32_t mpw_off(int r, int c) {
+  if constexpr (KC == 32) return sw64_off(r, c);
+  else return sw128_off(r, c);
+}
+template <int KC>
+__device__ __forceinline__ uint64_t mpw_desc(uint32_t saddr) {
+  if constexpr (KC == 32) return make_smem_desc64(saddr);
+  else return make_smem_desc(saddr);
+}
+
+// Wm [K, hidden] row-major fp32 -> bf16 tile images of Wm^T for the <KC = 64> geometry (128 hidden rows x 64 k, K-major, SW128)
+__global__ void __launch_bounds__(256) maxpool_pack128_kernel(const float* __restrict__ W, int64_t ldw, int K, int hidden,
+                                                              int kblocks, unsigned char* __restrict__ img) {
+  const int slice = blockIdx.x / kblocks, kb = blockIdx.x % kblocks;
+  unsigned char* dst = img + ((int64_t)slice * kblocks + kb) * (2 * MP_IMG);
+  for (int q = threadIdx.x; q < 128 * 8; q += blockDim.x) {
+    const int c = q >> 7, n = q & 127;
+    const int gn = slice * 128 + n, k0 = kb * 64 + c * 8;
+    __nv_bfloat162 h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float a = (gn < hidden && k0 + 2 * e < K) ? W[(int64_t)(k0 + 2 * e) * ldw + gn] : 0.f;
+      float b = (gn < hidden && k0 + 2 * e + 1 < K) ? W[(int64_t)(k0 + 2 * e + 1) * ldw + gn] : 0.f;
+      h[e] = __floats2bfloat162_rn(a, b);
+    }
+    *reinterpret_cast<uint4*>(dst + sw128_off(n, c)) = *reinterpret_cast<uint4*>(h);
+  }
+}
+
+__device__ __forceinline__ void tma_gather4(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int col, int r0, int r1,
+                                            int r2, int r3);
+
+// table row of tile row r of a CTA's local tile tl (padding rows of a tile read row 0: finite data the epilogue never
+// looks at)
+__device__ __forceinline__ int mpw_row_of(const MpParams& prm, int64_t tile0, int64_t tile_step, int64_t my_tiles,
+                                          int rows_valid, int64_t total_rows, int64_t tl, int r) {
+  const int64_t t = tile0 + tl * tile_step;
+  const int64_t flat = t * rows_valid + r;          // index into the (group, j) row list
+  int64_t id = 0;
+  if (tl < my_tiles && r < rows_valid && flat < total_rows) {
+    id = prm.row_ids ? (int64_t)prm.row_ids[flat] : prm.row0 + flat;
+    if (id < 0 || id >= prm.n_rows) id = prm.n_rows - 1;
+  }
+  return (int)id;
+}
+
+// cp.async gather producers: PW warps in two groups that alternate K-blocks (a group fills a whole stage, so two stages
+// are being filled at any time).  A thread owns one 16-byte chunk column of RPP-strided tile rows, keeps the row pointers
+// in registers and only adds the K-block step per copy.  Hand-off = cp.async groups + one elected arrive per warp, with
+// n_stages / 2 - 1 K-blocks in flight per thread; the generic->async proxy fence is on the consumer side.
+template <int KC, int NT, int PW>
+__device__ __forceinline__ void mpw_cpasync_producers(const MpParams& prm, int warp, int lane, int n_stages,
+                                                      unsigned char* x_ring, uint64_t* full_x, uint64_t* empty_x, int64_t tile0,
+                                                      int64_t tile_step, int64_t my_tiles, int rows_valid, int64_t total_rows) {
+  constexpr int ROWB = KC * 2;
+  constexpr int X_IMG = NT * ROWB;
+  const int kblocks = prm.kblocks;
+  auto row_of = [&](int64_t tl, int r) -> int { return mpw_row_of(prm, tile0, tile_step, my_tiles, rows_valid, total_rows, tl, r); };
+  {
+    constexpr int GT = PW * 32 / 2;               // threads per group
+    constexpr int TPR = ROWB / 16;                // threads per row piece (4 or 8)
+    constexpr int RPP = GT / TPR;                 // tile rows per pass of a group
+    constexpr int PASSES = NT / RPP;              // copies per thread per stage
+    static_assert(PASSES * RPP == NT && (PASSES == 8 || PASSES == 16), "a group fills a stage with 8 or 16 copies per thread");
+    const int grp = warp / (PW / 2);
+    const int tg = threadIdx.x - grp * GT;
+    const int c = tg % TPR, r0 = tg / TPR;
+    const uint32_t off0 = mpw_off<KC>(r0, c);     // + i * RPP * ROWB for pass i (the swizzle term only depends on r0)
+    const int64_t total_it = my_tiles * kblocks;
+    const int tail_bytes = (prm.K % KC) ? min(16, max(0, (prm.K - ((kblocks - 1) * KC + c * 8)) * 2)) : 16;
+    // Row ids are fetched a whole tile ahead in two steps: `request` only issues the loads (raw values, nothing depends on
+    // them), `finish` clamps them when the tile is reached.  (With load + clamp in one step ptxas consumed every id right
+    // after its load - eight serialised L2 round trips, ~4000 cycles, at every tile boundary.)
+    int raw[PASSES];
+    auto request = [&](int64_t tl) {
+      const int64_t t = tile0 + tl * tile_step;
+#pragma unroll
+      for (int i = 0; i < PASSES; ++i) {
+        const int r = r0 + RPP * i;
+        const int64_t flat = t * rows_valid + r;    // index into the (group, j) row list
+        const bool live = tl < my_tiles && r < rows_valid && flat < total_rows;
+        int v = 0;                                  // padding rows of a tile read row 0 (finite data, never looked at)
+        if (live) v = prm.row_ids ? __ldg(prm.row_ids + flat) : (int)(prm.row0 + flat);
+        raw[i] = v;
+      }
+    };
+    const unsigned char* rowp[PASSES];
+    auto finish = [&](int kb) {                     // clamp (as gs_gather_rows: out-of-range ids read the last row) -> row pointers
+#pragma unroll
+      for (int i = 0; i < PASSES; ++i) {
+        int id = raw[i];
+        if (id < 0 || (int64_t)id >= prm.n_rows) id = (int)(prm.n_rows - 1);
+        rowp[i] = reinterpret_cast<const unsigned char*>(prm.table + (int64_t)id * prm.pitch) + (size_t)kb * ROWB + c * 16;
+      }
+    };
+    int64_t tl = 0;
+    int kb = grp;
+    while (kb >= kblocks) { kb -= kblocks; ++tl; }
+    request(tl);
+    finish(kb);
+    request(tl + 1);
+    const int depth = min(6, max(1, n_stages / 2 - 1));   // K-blocks a group keeps in flight (its share of the ring minus one)
+    uint32_t s = grp % n_stages, ph = 0, s_old = s;
+    int pending = 0;
+    auto hand_over = [&]() {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_x[s_old]);
+      s_old += 2;
+      while (s_old >= (uint32_t)n_stages) s_old -= n_stages;
+      --pending;
+    };
+    for (int64_t it = grp; it < total_it; it += 2) {
+      mbar_wait(&empty_x[s], ph ^ 1u);
+      const uint32_t dst = smem_u32(x_ring + (size_t)s * X_IMG) + off0;
+      if (kb == kblocks - 1 && tail_bytes != 16) {
+#pragma unroll
+        for (int i = 0; i < PASSES; ++i)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + i * RPP * ROWB),
+                       "l"(tail_bytes ? (const void*)rowp[i] : (const void*)prm.table), "r"(tail_bytes) : "memory");
+      } else {
+#pragma unroll
+        for (int i = 0; i < PASSES; ++i)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * RPP * ROWB), "l"(rowp[i]) : "memory");
+      }
+      cp_async_commit();
+      if (++pending > depth) {
+        switch (depth) {                          // the oldest of this thread's K-blocks has landed
+          case 1: cp_async_wait<1>(); break;
+          case 2: cp_async_wait<2>(); break;
+          case 3: cp_async_wait<3>(); break;
+          case 4: cp_async_wait<4>(); break;
+          case 5: cp_async_wait<5>(); break;
+          default: cp_async_wait<6>(); break;
+        }
+        hand_over();
+      }
+      s += 2;
+      while (s >= (uint32_t)n_stages) { s -= n_stages; ph ^= 1u; }
+      kb += 2;
+      if (kb >= kblocks) {                        // next tile (two tiles on when a tile is a single K-block)
+        int adv = 0;
+        while (kb >= kblocks) { kb -= kblocks; ++adv; }
+        tl += adv;
+        if (adv != 1) request(tl);                // (single-K-block tiles: the prefetched tile is not the next one)
+        finish(kb);
+        request(tl + 1);                          // in flight while this tile's K-blocks are copied
+      } else {
+#pragma unroll
+        for (int i = 0; i < PASSES; ++i) rowp[i] += 2 * ROWB;
+      }
+    }
+    while (pending > 0) {                         // drain: hand the remaining K-blocks over, oldest first
+      switch (pending) {
+        case 1: cp_async_wait<0>(); break;
+        case 2: cp_async_wait<1>(); break;
+        case 3: cp_async_wait<2>(); break;
+        case 4: cp_async_wait<3>(); break;
+        case 5: cp_async_wait<4>(); break;
+        case 6: cp_async_wait<5>(); break;
+        default: cp_async_wait<6>(); break;
+      }
+      hand_over();
+    }
+  }
+}
+
+// PROD 0: cp.async gather producers - 8 warps in two groups that alternate K-blocks (a group fills a whole stage, so
+//         two stages are being filled at any time); a thread owns one 16-byte chunk column of RPP-strided tile rows,
+//         keeps the row pointers in registers and only adds the K-block step per copy (the first version recomputed
+//         addresses, tail predicates and swizzle offsets per copy: ~100 instructions per stage per warp, and with every
+//         warp taking part in every stage that instruction latency - not memory, not the barriers - set the stage rate:
+//         1070 cycles per stage against 256 cycles of MMA, identical with the copies removed);
+//         hand-off = cp.async groups + one elected arrive per warp; the generic->async proxy fence is consumer-side.
+// PROD 1: TMA producers - 4 warps, warp w owns ring slot w; per stage each lane issues ONE
+//         cp.async.bulk.tensor.2d.tile::gather4 (four table rows named by index, 128 bytes each, SWIZZLE_128B applied by
+//         the tensor map, columns >= K zero-filled) completing on the stage's mbarrier transaction count: no address
+//         arithmetic, no cp.async groups, no proxy fence, no arrives.  Needs NT == 128 (32 lanes x 4 rows) and 4 stages.
+template <int KC, int NT, int PROD>
+struct MpwCfg {
+  static constexpr int PW = PROD == 1 ? 4 : 8;             // producer warps
+  static constexpr int THREADS = (PW + 6) * 32;
+};
+
+template <int KC, int NT, int PROD>
+__global__ void __launch_bounds__(MpwCfg<KC, NT, PROD>::THREADS, 1)
+    maxpool_mlp_wide_kernel(const __grid_constant__ MpParams prm, const __grid_constant__ CUtensorMap tmap) {
+  constexpr int PW = MpwCfg<KC, NT, PROD>::PW;
+  constexpr int ROWB = KC * 2;                    // bytes of one operand row per K-block (64 or 128)
+  constexpr int W_IMG = 128 * ROWB;               // resident weight image of one K-block
+  constexpr int X_IMG = NT * ROWB;                // one X stage
+  static_assert(PROD == 0 || (NT == 128 && KC == 64), "the gather4 producers fill a 128-row SWIZZLE_128B stage per warp");
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_x[MPW_MAX_STAGES], empty_x[MPW_MAX_STAGES], acc_full[2], acc_empty[2], w_full;
+  __shared__ uint32_t tmem_base_smem;
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int kblocks = prm.kblocks;
+  const int n_stages = prm.n_stages;
+  unsigned char* w_res = smem;                                        // resident weight slice: kblocks images
+  unsigned char* x_ring = smem + MPW_SMEM_BYTES - (size_t)n_stages * X_IMG;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x % prm.n_slices;
+  const int64_t tile0 = blockIdx.x / prm.n_slices, tile_step = gridDim.x / prm.n_slices;
+  const int k = prm.k, G = prm.G;
+  const int rows_valid = G * k;
+  const int64_t total_rows = prm.n_groups * (int64_t)k;
+  const int64_t my_tiles = tile0 < prm.n_tiles ? (prm.n_tiles - tile0 + tile_step - 1) / tile_step : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MPW_MAX_STAGES; ++s) {
+      mbar_init(&full_x[s], PROD == 1 ? 1 : PW / 2);  // gather4: the expect_tx arrive; cp.async: one arrive per warp of the group
+      mbar_init(&empty_x[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);                  // one arrive per epilogue warp
+    }
+    mbar_init(&w_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == PW + 1) {
+    tmem_alloc(&tmem_base_smem, 2 * NT);            // two 128-lane x NT-column fp32 accumulators
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  auto row_of = [&](int64_t tl, int r) -> int { return mpw_row_of(prm, tile0, tile_step, my_tiles, rows_valid, total_rows, tl, r); };
+
+  if (warp < PW && prm.dbg != 3) {
+    if constexpr (PROD == 0) {
+      mpw_cpasync_producers<KC, NT, PW>(prm, warp, lane, n_stages, x_ring, full_x, empty_x, tile0, tile_step, my_tiles,
+                                        rows_valid, total_rows);
+    } else {
+      // =============================== gather producers (TMA tile::gather4) ===============================
+      const int64_t total_it = my_tiles * kblocks;
+      int cur[4], nxt[4];                           // table rows of this lane's tile rows 4 lane .. 4 lane + 3
+      auto load_ids = [&](int64_t tl, int (&ids)[4]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ids[i] = row_of(tl, 4 * lane + i);
+      };
+      int64_t tl = 0;
+      int kb = warp;
+      while (kb >= kblocks) { kb -= kblocks; ++tl; }
+      load_ids(tl, cur);
+      load_ids(tl + 1, nxt);
+      const int slot = warp;                        // this warp's ring slot (n_stages == PW)
+      uint32_t fill = 0;
+      for (int64_t it = warp; it < total_it; it += PW, ++fill) {
+        mbar_wait(&empty_x[slot], (fill & 1u) ^ 1u);
+        if (lane == 0) mbar_expect_tx(&full_x[slot], (uint32_t)X_IMG);
+        __syncwarp();
+        tma_gather4(x_ring + (size_t)slot * X_IMG + (size_t)lane * 4 * ROWB, &tmap, &full_x[slot], kb * KC, cur[0], cur[1],
+                    cur[2], cur[3]);
+        kb += PW;
+        if (kb >= kblocks) {
+          int adv = 0;
+          while (kb >= kblocks) { kb -= kblocks; ++adv; }
+          tl += adv;
+          if (adv == 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+          } else {
+            load_ids(tl, cur);
+          }
+          load_ids(tl + 1, nxt);
+        }
+      }
+    }
+  } else if (warp < PW) {
+    // timing probe: producers idle
+  } else if (warp == PW) {
+    // =============================== MMA issuer ===============================
+    constexpr uint32_t idesc = make_idesc(1u, 128, NT);               // bf16 x bf16 -> fp32, M = 128, N = NT
+    mbar_wait(&w_full, 0);
+    uint32_t s = 0, ph = 0, tcount = 0;
+    for (int64_t t = tile0; t < prm.n_tiles; t += tile_step, ++tcount) {
+      const uint32_t buf = tcount & 1u;
+      mbar_wait(&acc_empty[buf], ((tcount >> 1) & 1u) ^ 1u);          // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * (uint32_t)NT;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        if (prm.dbg != 3) {
+          mbar_wait(&full_x[s], ph);
+          if constexpr (PROD == 0) fence_proxy_async();               // cp.async wrote the stage through the generic proxy
+          tc_fence_after();
+        }
+        const uint64_t adesc = mpw_desc<KC>(smem_u32(w_res + (size_t)kb * W_IMG));
+        const uint64_t bdesc = mpw_desc<KC>(smem_u32(x_ring + (size_t)s * X_IMG));
+        if (prm.dbg != 4) {
+#pragma unroll
+          for (int k2 = 0; k2 < KC / 16; ++k2)      // K = 16 per instruction, 32 B apart inside the swizzle atom
+            umma_ss_elect<true>(tmem_acc, adesc + (uint64_t)(k2 * 2), bdesc + (uint64_t)(k2 * 2), idesc,
+                                (kb > 0 || k2 > 0) ? 1u : 0u);
+        }
+        umma_commit_elect(&empty_x[s]);
+        if (kb == kblocks - 1) umma_commit_elect(&acc_full[buf]);
+        __syncwarp();
+        if (++s == (uint32_t)n_stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == PW + 1) {
+    // =============================== resident weight slice ===============================
+    if (lane == 0) {
+      mbar_expect_tx(&w_full, (uint32_t)(kblocks * W_IMG));
+      const unsigned char* src = prm.wimg + (int64_t)slice * kblocks * W_IMG;
+      for (int kb = 0; kb < kblocks; ++kb) bulk_g2s(w_res + (size_t)kb * W_IMG, src + (int64_t)kb * W_IMG, W_IMG, &w_full);
+    }
+    __syncwarp();
+  } else {
+    // =============================== epilogue ===============================
+    const int q = warp & 3;                         // TMEM lane quarter of this warp (four consecutive warps cover 0..3)
+    const int h = slice * 128 + q * 32 + lane;      // this thread's hidden unit = its TMEM lane
+    const float b = prm.bias ? prm.bias[h] : 0.f;
+    const float inv_k = 1.0f / (float)k;
+    uint32_t tcount = 0;
+    for (int64_t t = tile0; t < prm.n_tiles; t += tile_step, ++tcount) {
+      const uint32_t buf = tcount & 1u;
+      const int64_t g_base = t * G;
+      const int groups_here = (int)min((int64_t)G, prm.n_groups - g_base);
+      mbar_wait(&acc_full[buf], (tcount >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * (uint32_t)NT + ((uint32_t)(q * 32) << 16);
+      float* outp = prm.out + g_base * prm.ldo + h;
+      // One fanout group = k consecutive accumulator columns of this lane.  Each group is fetched from TMEM by itself, in
+      // pieces of 32 / 16 / 8 / 4 / 2 / 1 columns chosen by the bits of k (k = 25: x16 + x8 + x1), so every register is
+      // statically indexed and the pooling is straight-line FMNMX / FADD code; only the piece selection branches, and
+      // that is warp-uniform.  (Pooling fixed 32-column chunks with a running counter cost a compare + branch region per
+      // ELEMENT: the four epilogue warps were busy 85 % of the kernel and, not the producers, set the tile rate.)
+      const bool mean = prm.pool_mean != 0;
+      auto fold = [&](float m, uint32_t x) -> float {
+        const float v = __uint_as_float(x);
+        // mean-pool (reference aggregators.py:246-273): ReLU does not commute with the mean, so bias + ReLU are applied
+        // per element and summed in j order; max-pool: bias + ReLU after the max (they commute with it)
+        return mean ? m + fmaxf(v + b, 0.f) : fmaxf(m, v);
+      };
+      for (int g = 0; g < groups_here; ++g) {
+        uint32_t col = tmem_acc + (uint32_t)(g * k);
+        float m = mean ? 0.f : -3.0e38f;
+        int rem = k;
+        while (rem >= 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(col, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m = fold(m, r[j]);
+          col += 32u;
+          rem -= 32;
+        }
+        uint32_t r16[16], r8[8], r4[4], r2[2], r1[1];
+        uint32_t cc = col;
+        if (rem & 16) { tmem_ld_32x16(cc, r16); cc += 16u; }
+        if (rem & 8) { tmem_ld_32x8(cc, r8); cc += 8u; }
+        if (rem & 4) { tmem_ld_32x4(cc, r4); cc += 4u; }
+        if (rem & 2) { tmem_ld_32x2(cc, r2); cc += 2u; }
+        if (rem & 1) { tmem_ld_32x1(cc, r1); }
+        tmem_ld_wait();
+        if (rem & 16) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) m = fold(m, r16[j]);
+        }
+        if (rem & 8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) m = fold(m, r8[j]);
+        }
+        if (rem & 4) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) m = fold(m, r4[j]);
+        }
+        if (rem & 2) {
+          m = fold(m, r2[0]);
+          m = fold(m, r2[1]);
+        }
+        if (rem & 1) m = fold(m, r1[0]);
+        outp[(int64_t)g * prm.ldo] = mean ? m * inv_k : fmaxf(m + b, 0.f);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  __syncthreads();
+  if (warp == PW + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * NT);
+  }
+}
+
+// cp.async gather producers for the two-pipeline kernel: group g (PW / 2 warps) serves pipeline g alone - the CTA's local
+// tiles g, g + 2, ... - through its own ring of n_half stages (full / empty barriers and stage memory passed in already
+// offset).  Otherwise as mpw_cpasync_producers: a thread owns one 16-byte chunk column of RPP-strided tile rows, row
+// pointers stay in registers, ids are requested a tile ahead, hand-off by cp.async groups + one elected arrive per warp.
+template <int KC, int NT, int PW>
+__device__ __forceinline__ void mpw_cpasync_pipeline_producers(const MpParams& prm, int grp, int tg, int lane, int n_half,
+                                                               unsigned char* ring, uint64_t* full_x, uint64_t* empty_x,
+                                                               int64_t tile0, int64_t tile_step, int64_t my_tiles,
+                                                               int rows_valid, int64_t total_rows) {
+  constexpr int ROWB = KC * 2;
+  constexpr int X_IMG = NT * ROWB;
+  constexpr int GT = PW * 32 / 2;                 // threads per group
+  constexpr int TPR = ROWB / 16;                  // threads per row piece
+  constexpr int RPP = GT / TPR;                   // tile rows per pass of a group
+  constexpr int PASSES = NT / RPP;                // copies per thread per stage
+  static_assert(PASSES * RPP == NT && (PASSES == 8 || PASSES == 16), "a group fills a stage with 8 or 16 copies per thread");
+  const int kblocks = prm.kblocks;
+  const int c = tg % TPR, r0 = tg / TPR;
+  const uint32_t off0 = mpw_off<KC>(r0, c);
+  const int tail_bytes = (prm.K % KC) ? min(16, max(0, (prm.K - ((kblocks - 1) * KC + c * 8)) * 2)) : 16;
+  int raw[PASSES];
+  auto request = [&](int64_t tl) {
+    const int64_t t = tile0 + tl * tile_step;
+#pragma unroll
+    for (int i = 0; i < PASSES; ++i) {
+      const int r = r0 + RPP * i;
+      const int64_t flat = t * rows_valid + r;
+      const bool live = tl < my_tiles && r < rows_valid && flat < total_rows;
+      int v = 0;
+      if (live) v = prm.row_ids ? __ldg(prm.row_ids + flat) : (int)(prm.row0 + flat);
+      raw[i] = v;
+    }
+  };
+  const unsigned char* rowp[PASSES];
+  auto finish = [&]() {
+#pragma unroll
+    for (int i = 0; i < PASSES; ++i) {
+      int id = raw[i];
+      if (id < 0 || (int64_t)id >= prm.n_rows) id = (int)(prm.n_rows - 1);
+      rowp[i] = reinterpret_cast<const unsigned char*>(prm.table + (int64_t)id * prm.pitch) + c * 16;
+    }
+  };
+  const int depth = min(6, max(1, n_half - 1));   // K-blocks kept in flight per thread
+  uint32_t s = 0, ph = 0, s_old = 0;
+  int pending = 0;
+  auto hand_over = [&]() {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&full_x[s_old]);
+    if (++s_old == (uint32_t)n_half) s_old = 0;
+    --pending;
+  };
+  request(grp);
+  for (int64_t tl = grp; tl < my_tiles; tl += 2) {
+    finish();
+    request(tl + 2);                              // in flight while this tile's K-blocks are copied
+    for (int kb = 0; kb < kblocks; ++kb) {
+      mbar_wait(&empty_x[s], ph ^ 1u);
+      const uint32_t dst = smem_u32(ring + (size_t)s * X_IMG) + off0;
+      if (kb == kblocks - 1 && tail_bytes != 16) {
+#pragma unroll
+        for (int i = 0; i < PASSES; ++i)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + i * RPP * ROWB),
+                       "l"(tail_bytes ? (const void*)rowp[i] : (const void*)prm.table), "r"(tail_bytes) : "memory");
+      } else {
+#pragma unroll
+        for (int i = 0; i < PASSES; ++i)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * RPP * ROWB), "l"(rowp[i]) : "memory");
+      }
+      cp_async_commit();
+      if (++pending > depth) {
+        switch (depth) {
+          case 1: cp_async_wait<1>(); break;
+          case 2: cp_async_wait<2>(); break;
+          case 3: cp_async_wait<3>(); break;
+          case 4: cp_async_wait<4>(); break;
+          case 5: cp_async_wait<5>(); break;
+          default: cp_async_wait<6>(); break;
+        }
+        hand_over();
+      }
+      if (++s == (uint32_t)n_half) { s = 0; ph ^= 1u; }
+#pragma unroll
+      for (int i = 0; i < PASSES; ++i) rowp[i] += ROWB;
+    }
+  }
+  while (pending > 0) {
+    switch (pending) {
+      case 1: cp_async_wait<0>(); break;
+      case 2: cp_async_wait<1>(); break;
+      case 3: cp_async_wait<2>(); break;
+      case 4: cp_async_wait<3>(); break;
+      case 5: cp_async_wait<4>(); break;
+      case 6: cp_async_wait<5>(); break;
+      default: cp_async_wait<6>(); break;
+    }
+    hand_over();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K4, "tmem" form (k4_kernel = 0, the default): the wide form with the resident weight slice moved out of shared memory.
+// What the wide kernels showed (tools/k4_matrix.py probes): with the 160 KB weight slice resident in shared memory only
+// FOUR 16 KB operand stages fit, and one trip of a stage round the ring - issue the gather, the data lands, the MMA warp
+// wakes, the MMAs retire, the commit frees the slot, the producers wake - takes ~4000 cycles whatever the producer
+// mechanism (cp.async, hardware-fired arrives, TMA gather4) and even with the copies removed: ~1000 cycles per stage
+// against 256 cycles of MMA.  The cure is more stages in flight, and the place for the weights is tensor memory:
+//   * the A operand of tcgen05.mma may live in TMEM (TS form).  A = this CTA's slice of Wm^T (128 hidden units = 128
+//     lanes; bf16 pairs, K / 2 columns): the first kb_t <= 8 K-blocks (256 columns) sit in TMEM beside the two 128-column
+//     accumulators, written once per CTA by the epilogue warps with tcgen05.st; any further K-blocks stay in shared memory
+//     (SS form) - K = 602 -> 8 in TMEM + 2 in shared memory;
+//   * shared memory then holds 12 operand stages (192 KB in flight per SM) instead of 4;
+//   * the MMA warp's waits are warp votes (mbar_wait_uniform) so that descriptor arithmetic stays in uniform registers:
+//     with a divergent wait loop in front of them ptxas wrapped every tcgen05.mma in R2UR + ELECT + VOTEU sequences and
+//     the issue loop alone ran at 154 cycles per MMA (64 is the tensor pipe's floor).
+// Geometry: 128-row tiles, 64-column K-blocks (128-byte row pieces, SWIZZLE_128B); producers = mpw_cpasync_producers.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int MPT_MAX_STAGES = 14;
+constexpr int MPT_PW = 8;
+constexpr int MPT_THREADS = (MPT_PW + 6) * 32;
+constexpr int MPT_IMG = 128 * 128;                // one K-block image: 128 rows x 128 B
+constexpr int MPT_ACOL0 = 256;                    // TMEM columns [0, 256): two accumulators; [256, 256 + 32 kb_t): weights
+constexpr int MPT_MAX_KB_T = 8;
+
+// Wm [K, hidden] row-major fp32 -> wT[hidden_padded][kblocks * 32] uint32: word j of row h = bf16(W[2j, h]) | bf16(W[2j+1, h]) << 16
+__global__ void __launch_bounds__(256) maxpool_pack_rows_kernel(const float* __restrict__ W, int64_t ldw, int K, int hidden,
+                                                                int words, uint32_t* __restrict__ out) {
+  const int64_t total = (int64_t)gridDim.y * 128 * words;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < (int64_t)128 * words; q += (int64_t)gridDim.x * blockDim.x) {
+    const int hl = (int)(q % 128), j = (int)(q / 128);          // hidden fastest: coalesced reads of W rows
+    const int h = blockIdx.y * 128 + hl;
+    const float a = (h < hidden && 2 * j < K) ? W[(int64_t)(2 * j) * ldw + h] : 0.f;
+    const float b = (h < hidden && 2 * j + 1 < K) ? W[(int64_t)(2 * j + 1) * ldw + h] : 0.f;
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    out[((int64_t)blockIdx.y * 128 + hl) * words + j] = *reinterpret_cast<const uint32_t*>(&v);
+  }
+  (void)total;
+}
+
+// NT = 128: two 128-column accumulators (the epilogue of tile t overlaps the MMAs of tile t + 1).
+// NT = 256 (default): ONE 256-column accumulator and 256-row tiles.  The MMA warp - a single warp - needs ~860 cycles of
+// waits, fences, descriptor moves and commits per four-MMA K-block whatever N is (measured: with NT = 128 it was never
+// waiting for operands any more, yet the tensor pipe idled 70 % of the time); N = 256 doubles the tensor work behind each
+// of those instructions (128 cycles per MMA instead of 64).  The price is that the epilogue of a tile is no longer
+// hidden behind the next tile's MMAs (TMEM has no room for a second 256-column accumulator beside the weights).
+template <int NT>
+__global__ void __launch_bounds__(MPT_THREADS, 1) maxpool_mlp_tmem_kernel(const __grid_constant__ MpParams prm) {
+  constexpr int KC = 64;
+  constexpr int NBUF = NT == 128 ? 2 : 1;
+  constexpr int X_IMG = NT * 128;
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_x[MPT_MAX_STAGES], empty_x[MPT_MAX_STAGES], acc_full[2], acc_empty[2], w_full, wt_full;
+  __shared__ uint32_t tmem_base_smem;
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int kblocks = prm.kblocks, kb_t = prm.kb_t, kb_s = kblocks - kb_t;
+  const int n_stages = prm.n_stages;
+  unsigned char* w_res = smem;                                        // K-blocks kb_t.. of the weight slice (SS operands)
+  unsigned char* x_ring = smem + (size_t)kb_s * MPT_IMG;     // n_stages stages of X_IMG bytes
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x % prm.n_slices;
+  const int64_t tile0 = blockIdx.x / prm.n_slices, tile_step = gridDim.x / prm.n_slices;
+  const int k = prm.k, G = prm.G;
+  const int rows_valid = G * k;
+  const int64_t total_rows = prm.n_groups * (int64_t)k;
+  const int64_t my_tiles = tile0 < prm.n_tiles ? (prm.n_tiles - tile0 + tile_step - 1) / tile_step : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MPT_MAX_STAGES; ++s) {
+      mbar_init(&full_x[s], MPT_PW / 2);            // one arrive per warp of the filling group
+      mbar_init(&empty_x[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);                  // one arrive per epilogue warp
+    }
+    mbar_init(&w_full, 1);
+    mbar_init(&wt_full, 4);                         // one arrive per epilogue warp (each writes its 32 TMEM lanes)
+    fence_mbar_init();
+  }
+  if (warp == MPT_PW + 1) {
+    tmem_alloc(&tmem_base_smem, 512);               // 2 x 128 accumulator columns + up to 256 weight columns
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp < MPT_PW) {
+    mpw_cpasync_producers<KC, NT, MPT_PW>(prm, warp, lane, n_stages, x_ring, full_x, empty_x, tile0, tile_step, my_tiles,
+                                          rows_valid, total_rows);
+  } else if (warp == MPT_PW) {
+    // =============================== MMA issuer ===============================
+    constexpr uint32_t idesc = make_idesc(1u, 128, NT);               // bf16 x bf16 -> fp32, M = 128, N = 128
+    if (kb_s > 0) mbar_wait_uniform(&w_full, 0);
+    if (kb_t > 0) mbar_wait_uniform(&wt_full, 0);
+    tc_fence_after();
+    const uint32_t x_base = smem_u32(x_ring), w_base = smem_u32(w_res);
+    uint32_t s = 0, ph = 0;
+    for (int64_t tl = 0; tl < my_tiles; ++tl) {
+      const uint32_t buf = NBUF == 2 ? ((uint32_t)tl & 1u) : 0u;
+      const uint32_t use = (uint32_t)(NBUF == 2 ? (tl >> 1) : tl);          // how often this accumulator has been used before
+      mbar_wait_uniform(&acc_empty[buf], (use & 1u) ^ 1u);                  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * (uint32_t)NT;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait_uniform(&full_x[s], ph);
+        fence_proxy_async();                        // cp.async wrote the stage through the generic proxy
+        tc_fence_after();
+        const uint64_t bdesc = make_smem_desc(x_base + s * (uint32_t)X_IMG);
+        if (kb < kb_t) {
+          const uint32_t a_t = tmem_base + (uint32_t)MPT_ACOL0 + (uint32_t)kb * 32u;
+#pragma unroll
+          for (int k2 = 0; k2 < KC / 16; ++k2)      // K = 16 per instruction: 8 TMEM columns of A, 32 B of B inside the atom
+            umma_ts_elect_bf16(tmem_acc, a_t + (uint32_t)(k2 * 8), bdesc + (uint64_t)(k2 * 2), idesc, (kb > 0 || k2 > 0) ? 1u : 0u);
+        } else {
+          const uint64_t adesc = make_smem_desc(w_base + (uint32_t)(kb - kb_t) * (uint32_t)MPT_IMG);
+#pragma unroll
+          for (int k2 = 0; k2 < KC / 16; ++k2)
+            umma_ss_elect<true>(tmem_acc, adesc + (uint64_t)(k2 * 2), bdesc + (uint64_t)(k2 * 2), idesc, (kb > 0 || k2 > 0) ? 1u : 0u);
+        }
+        umma_commit_elect(&empty_x[s]);
+        if (kb == kblocks - 1) umma_commit_elect(&acc_full[buf]);
+        if (++s == (uint32_t)n_stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == MPT_PW + 1) {
+    // =============================== shared-memory part of the weight slice ===============================
+    if (lane == 0 && kb_s > 0) {
+      mbar_expect_tx(&w_full, (uint32_t)(kb_s * MPT_IMG));
+      const unsigned char* src = prm.wimg + ((int64_t)slice * kblocks + kb_t) * MPT_IMG;
+      for (int kb = 0; kb < kb_s; ++kb) bulk_g2s(w_res + (size_t)kb * MPT_IMG, src + (int64_t)kb * MPT_IMG, MPT_IMG, &w_full);
+    }
+    __syncwarp();
+  } else {
+    // =============================== epilogue warps ===============================
+    const int q = warp & 3;                         // TMEM lane quarter of this warp (four consecutive warps cover 0..3)
+    const int h = slice * 128 + q * 32 + lane;      // this thread's hidden unit = its TMEM lane
+    // once: this lane's row of Wm^T (bf16 pairs) for the first kb_t K-blocks -> tensor memory (A operand, TS form)
+    {
+      const uint32_t* wrow = prm.wrows + (int64_t)h * (kblocks * 32);
+      const uint32_t t_a = tmem_base + (uint32_t)MPT_ACOL0 + ((uint32_t)(q * 32) << 16);
+      for (int cb = 0; cb < kb_t; ++cb) {
+        uint32_t r[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(wrow + cb * 32) + j);
+          r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
+        }
+        tmem_st_32x32(t_a + (uint32_t)(cb * 32), r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&wt_full);
+    }
+    const float b = prm.bias ? prm.bias[h] : 0.f;
+    const float inv_k = 1.0f / (float)k;
+    const bool mean = prm.pool_mean != 0;
+    auto fold = [&](float m, uint32_t x) -> float {
+      const float v = __uint_as_float(x);
+      // mean-pool (reference aggregators.py:246-273): ReLU does not commute with the mean, so bias + ReLU are applied
+      // per element and summed in j order; max-pool: bias + ReLU after the max (they commute with it)
+      return mean ? m + fmaxf(v + b, 0.f) : fmaxf(m, v);
+    };
+    for (int64_t tl = 0; tl < my_tiles; ++tl) {
+      const int64_t t = tile0 + tl * tile_step;
+      const uint32_t buf = NBUF == 2 ? ((uint32_t)tl & 1u) : 0u;
+      const uint32_t use = (uint32_t)(NBUF == 2 ? (tl >> 1) : tl);
+      const int64_t g_base = t * G;
+      const int groups_here = (int)min((int64_t)G, prm.n_groups - g_base);
+      mbar_wait(&acc_full[buf], use & 1u);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * (uint32_t)NT + ((uint32_t)(q * 32) << 16);
+      float* outp = prm.out + g_base * prm.ldo + h;
+      // one fanout group = k consecutive accumulator columns of this lane, fetched in pieces of 32 / 16 / 8 / 4 / 2 / 1
+      // columns chosen by the bits of k: statically indexed registers, straight-line pooling (see the wide kernel)
+      for (int g = 0; g < groups_here; ++g) {
+        uint32_t col = tmem_acc + (uint32_t)(g * k);
+        float m = mean ? 0.f : -3.0e38f;
+        int rem = k;
+        while (rem >= 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(col, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m = fold(m, r[j]);
+          col += 32u;
+          rem -= 32;
+        }
+        uint32_t r16[16], r8[8], r4[4], r2[2], r1[1];
+        uint32_t cc = col;
+        if (rem & 16) { tmem_ld_32x16(cc, r16); cc += 16u; }
+        if (rem & 8) { tmem_ld_32x8(cc, r8); cc += 8u; }
+        if (rem & 4) { tmem_ld_32x4(cc, r4); cc += 4u; }
+        if (rem & 2) { tmem_ld_32x2(cc, r2); cc += 2u; }
+        if (rem & 1) { tmem_ld_32x1(cc, r1); }
+        tmem_ld_wait();
+        if (rem & 16) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) m = fold(m, r16[j]);
+        }
+        if (rem & 8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) m = fold(m, r8[j]);
+        }
+        if (rem & 4) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) m = fold(m, r4[j]);
+        }
+        if (rem & 2) {
+          m = fold(m, r2[0]);
+          m = fold(m, r2[1]);
+        }
+        if (rem & 1) m = fold(m, r1[0]);
+        outp[(int64_t)g * prm.ldo] = mean ? m * inv_k : fmaxf(m + b, 0.f);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  __syncthreads();
+  if (warp == MPT_PW + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// Two pipelines per CTA (k4_kernel = 0 with k4_tile = 128 and k4_pipes = 2, the default): the NT = 128 kernel showed the
+// single MMA warp saturated - ~860 cycles of instruction latency per four-MMA K-block, tensor pipe idle 70 % - and never
+// short of operands.  Here the CTA runs TWO independent producer -> MMA chains that share only the weights in TMEM, the
+// tensor pipe and the epilogue warps: chain p = producer group p (4 warps) -> its own half of the operand ring -> MMA warp
+// p -> accumulator p, working on the CTA's local tiles p, p + 2, ...  The tensor pipe interleaves the two accumulation
+// chains (they are independent), so two issuing warps double the MMA issue rate.
+__global__ void __launch_bounds__(MPT_THREADS, 1) maxpool_mlp_tmem2_kernel(const __grid_constant__ MpParams prm) {
+  constexpr int KC = 64, NT = 128;
+  constexpr int X_IMG = NT * 128;
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_x[MPT_MAX_STAGES], empty_x[MPT_MAX_STAGES], acc_full[2], acc_empty[2], w_full, wt_full;
+  __shared__ uint32_t tmem_base_smem;
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int kblocks = prm.kblocks, kb_t = prm.kb_t, kb_s = kblocks - kb_t;
+  const int n_stages = prm.n_stages;
+  unsigned char* w_res = smem;                                        // K-blocks kb_t.. of the weight slice (SS operands)
+  unsigned char* x_ring = smem + (size_t)kb_s * MPT_IMG;     // n_stages stages of X_IMG bytes
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x % prm.n_slices;
+  const int64_t tile0 = blockIdx.x / prm.n_slices, tile_step = gridDim.x / prm.n_slices;
+  const int k = prm.k, G = prm.G;
+  const int rows_valid = G * k;
+  const int64_t total_rows = prm.n_groups * (int64_t)k;
+  const int64_t my_tiles = tile0 < prm.n_tiles ? (prm.n_tiles - tile0 + tile_step - 1) / tile_step : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MPT_MAX_STAGES; ++s) {
+      mbar_init(&full_x[s], MPT_PW / 2);            // one arrive per warp of the pipeline's producer group
+      mbar_init(&empty_x[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);                  // one arrive per epilogue warp
+    }
+    mbar_init(&w_full, 1);
+    mbar_init(&wt_full, 4);                         // one arrive per epilogue warp (each writes its 32 TMEM lanes)
+    fence_mbar_init();
+  }
+  if (warp == MPT_PW) {
+    tmem_alloc(&tmem_base_smem, 512);               // 2 x 128 accumulator columns + up to 256 weight columns
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int n_half = n_stages / 2;                  // stages per pipeline
+  if (warp < MPT_PW) {
+    const int grp = warp / (MPT_PW / 2);
+    mpw_cpasync_pipeline_producers<KC, NT, MPT_PW>(prm, grp, (int)threadIdx.x - grp * (MPT_PW * 16), lane, n_half,
+                                                   x_ring + (size_t)grp * n_half * X_IMG, full_x + grp * n_half,
+                                                   empty_x + grp * n_half, tile0, tile_step, my_tiles, rows_valid, total_rows);
+  } else if (warp == MPT_PW || warp == MPT_PW + 1) {
+    const int pipe = warp - MPT_PW;
+    if (pipe == 1 && lane == 0 && kb_s > 0) {       // shared-memory part of the weight slice (once)
+      mbar_expect_tx(&w_full, (uint32_t)(kb_s * MPT_IMG));
+      const unsigned char* src = prm.wimg + ((int64_t)slice * kblocks + kb_t) * MPT_IMG;
+      for (int kb = 0; kb < kb_s; ++kb) bulk_g2s(w_res + (size_t)kb * MPT_IMG, src + (int64_t)kb * MPT_IMG, MPT_IMG, &w_full);
+    }
+    __syncwarp();
+    // =============================== MMA issuer ===============================
+    constexpr uint32_t idesc = make_idesc(1u, 128, NT);               // bf16 x bf16 -> fp32, M = 128, N = 128
+    if (kb_s > 0) mbar_wait_uniform(&w_full, 0);
+    if (kb_t > 0) mbar_wait_uniform(&wt_full, 0);
+    tc_fence_after();
+    const uint32_t x_base = smem_u32(x_ring + (size_t)pipe * n_half * X_IMG), w_base = smem_u32(w_res);
+    uint64_t* full_p = full_x + pipe * n_half;
+    uint64_t* empty_p = empty_x + pipe * n_half;
+    uint32_t s = 0, ph = 0;
+    for (int64_t tl = pipe; tl < my_tiles; tl += 2) {
+      const uint32_t buf = (uint32_t)pipe;
+      const uint32_t use = (uint32_t)(tl >> 1);                             // how often this accumulator has been used before
+      mbar_wait_uniform(&acc_empty[buf], (use & 1u) ^ 1u);                  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * (uint32_t)NT;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait_uniform(&full_p[s], ph);
+        fence_proxy_async();                        // cp.async wrote the stage through the generic proxy
+        tc_fence_after();
+        const uint64_t bdesc = make_smem_desc(x_base + s * (uint32_t)X_IMG);
+        if (kb < kb_t) {
+          const uint32_t a_t = tmem_base + (uint32_t)MPT_ACOL0 + (uint32_t)kb * 32u;
+#pragma unroll
+          for (int k2 = 0; k2 < KC / 16; ++k2)      // K = 16 per instruction: 8 TMEM columns of A, 32 B of B inside the atom
+            umma_ts_elect_bf16(tmem_acc, a_t + (uint32_t)(k2 * 8), bdesc + (uint64_t)(k2 * 2), idesc, (kb > 0 || k2 > 0) ? 1u : 0u);
+        } else {
+          const uint64_t adesc = make_smem_desc(w_base + (uint32_t)(kb - kb_t) * (uint32_t)MPT_IMG);
+#pragma unroll
+          for (int k2 = 0; k2 < KC / 16; ++k2)
+            umma_ss_elect<true>(tmem_acc, adesc + (uint64_t)(k2 * 2), bdesc + (uint64_t)(k2 * 2), idesc, (kb > 0 || k2 > 0) ? 1u : 0u);
+        }
+        umma_commit_elect(&empty_p[s]);
+        if (kb == kblocks - 1) umma_commit_elect(&acc_full[buf]);
+        if (++s == (uint32_t)n_half) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // =============================== epilogue warps ===============================
+    const int q = warp & 3;                         // TMEM lane quarter of this warp (four consecutive warps cover 0..3)
+    const int h = slice * 128 + q * 32 + lane;      // this thread's hidden unit = its TMEM lane
+    // once: this lane's row of Wm^T (bf16 pairs) for the first kb_t K-blocks -> tensor memory (A operand, TS form)
+    {
+      const uint32_t* wrow = prm.wrows + (int64_t)h * (kblocks * 32);
+      const uint32_t t_a = tmem_base + (uint32_t)MPT_ACOL0 + ((uint32_t)(q * 32) << 16);
+      for (int cb = 0; cb < kb_t; ++cb) {
+        uint32_t r[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(wrow + cb * 32) + j);
+          r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
+        }
+        tmem_st_32x32(t_a + (uint32_t)(cb * 32), r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&wt_full);
+    }
+    const float b = prm.bias ? prm.bias[h] : 0.f;
+    const float inv_k = 1.0f / (float)k;
+    const bool mean = prm.pool_mean != 0;
+    auto fold = [&](float m, uint32_t x) -> float {
+      const float v = __uint_as_float(x);
+      // mean-pool (reference aggregators.py:246-273): ReLU does not commute with the mean, so bias + ReLU are applied
+      // per element and summed in j order; max-pool: bias + ReLU after the max (they commute with it)
+      return mean ? m + fmaxf(v + b, 0.f) : fmaxf(m, v);
+    };
+    for (int64_t tl = 0; tl < my_tiles; ++tl) {
+      const int64_t t = tile0 + tl * tile_step;
+      const uint32_t buf = (uint32_t)tl & 1u;
+      const uint32_t use = (uint32_t)(tl >> 1);
+      const int64_t g_base = t * G;
+      const int groups_here = (int)min((int64_t)G, prm.n_groups - g_base);
+      mbar_wait(&acc_full[buf], use & 1u);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * (uint32_t)NT + ((uint32_t)(q * 32) << 16);
+      float* outp = prm.out + g_base * prm.ldo + h;
+      // one fanout group = k consecutive accumulator columns of this lane, fetched in pieces of 32 / 16 / 8 / 4 / 2 / 1
+      // columns chosen by the bits of k: statically indexed registers, straight-line pooling (see the wide kernel)
+      for (int g = 0; g < groups_here; ++g) {
+        uint32_t col = tmem_acc + (uint32_t)(g * k);
+        float m = mean ? 0.f : -3.0e38f;
+        int rem = k;
+        while (rem >= 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(col, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m = fold(m, r[j]);
+          col += 32u;
+          rem -= 32;
+        }
+        uint32_t r16[16], r8[8], r4[4], r2[2], r1[1];
+        uint32_t cc = col;
+        if (rem & 16) { tmem_ld_32x16(cc, r16); cc += 16u; }
+        if (rem & 8) { tmem_ld_32x8(cc, r8); cc += 8u; }
+        if (rem & 4) { tmem_ld_32x4(cc, r4); cc += 4u; }
+        if (rem & 2) { tmem_ld_32x2(cc, r2); cc += 2u; }
+        if (rem & 1) { tmem_ld_32x1(cc, r1); }
+        tmem_ld_wait();
+        if (rem & 16) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) m = fold(m, r16[j]);
+        }
+        if (rem & 8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) m = fold(m, r8[j]);
+        }
+        if (rem & 4) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) m = fold(m, r4[j]);
+        }
+        if (rem & 2) {
+          m = fold(m, r2[0]);
+          m = fold(m, r2[1]);
+        }
+        if (rem & 1) m = fold(m, r1[0]);
+        outp[(int64_t)g * prm.ldo] = mean ? m * inv_k : fmaxf(m + b, 0.f);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  __syncthreads();
+  if (warp == MPT_PW) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Variant (GS_TUNING=k4_producer=1, not the default until measured): the gather-A producers use the TMA's row gather,
 // `cp.async.bulk.tensor.2d.tile::gather4` - one instruction fetches a 64-byte K-block segment of FOUR table rows named
 // by index and writes them, SWIZZLE_64B applied by the tensor map, straight into the UMMA stage; completion is the
@@ -663,25 +1609,43 @@ int32_t gs_debug_read_maxpool_timeline(unsigned long long* out_host, int32_t n) 
   return GS_OK;
 }
 
-int64_t gs_maxpool_mlp_workspace_bytes(int32_t K, int32_t hidden) {
-  if (K < 1 || hidden < 1) return -1;
+// packed weights = region 0: [slices][ceil(K/32)] images of 128 x 64 B (SW64) | region 1: [slices][ceil(K/64)] images of
+// 128 x 128 B (SW128); every kernel geometry finds its own format (packing is per weight update, not per step)
+static int64_t mp_region0_bytes(int32_t K, int32_t hidden) {
   const int kblocks = (K + gs::MP_KCOLS - 1) / gs::MP_KCOLS, slices = (hidden + 127) / 128;
   return (int64_t)kblocks * slices * gs::MP_IMG;
+}
+
+static int64_t mp_region1_bytes(int32_t K, int32_t hidden) {
+  const int kb128 = (K + 63) / 64, slices = (hidden + 127) / 128;
+  return (int64_t)kb128 * slices * 2 * gs::MP_IMG;
+}
+
+// region 2: Wm^T as rows of bf16 pairs, [slices * 128][ceil(K/64) * 32] uint32 (what the tmem kernel stores into TMEM)
+int64_t gs_maxpool_mlp_workspace_bytes(int32_t K, int32_t hidden) {
+  if (K < 1 || hidden < 1) return -1;
+  const int kb128 = (K + 63) / 64, slices = (hidden + 127) / 128;
+  return mp_region0_bytes(K, hidden) + mp_region1_bytes(K, hidden) + (int64_t)slices * 128 * kb128 * 32 * 4;
 }
 
 int32_t gs_maxpool_mlp_pack(const float* Wm, int64_t ldw, int32_t K, int32_t hidden, void* workspace, void* stream) {
   GS_REQUIRE(Wm && workspace && K >= 1 && hidden >= 1 && ldw >= hidden, "gs_maxpool_mlp_pack: bad arguments");
   GS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 127u) == 0, "gs_maxpool_mlp_pack: workspace must be 128-byte aligned");
-  const int kblocks = (K + gs::MP_KCOLS - 1) / gs::MP_KCOLS, slices = (hidden + 127) / 128;
-  gs::maxpool_pack_kernel<<<kblocks * slices, 256, 0, (cudaStream_t)stream>>>(Wm, ldw, K, hidden, kblocks,
-                                                                             (unsigned char*)workspace);
+  const int kblocks = (K + gs::MP_KCOLS - 1) / gs::MP_KCOLS, slices = (hidden + 127) / 128, kb128 = (K + 63) / 64;
+  unsigned char* ws = (unsigned char*)workspace;
+  gs::maxpool_pack_kernel<<<kblocks * slices, 256, 0, (cudaStream_t)stream>>>(Wm, ldw, K, hidden, kblocks, ws);
+  gs::maxpool_pack128_kernel<<<kb128 * slices, 256, 0, (cudaStream_t)stream>>>(Wm, ldw, K, hidden, kb128,
+                                                                               ws + mp_region0_bytes(K, hidden));
+  gs::maxpool_pack_rows_kernel<<<dim3(8, slices), 256, 0, (cudaStream_t)stream>>>(
+      Wm, ldw, K, hidden, kb128 * 32, (uint32_t*)(ws + mp_region0_bytes(K, hidden) + mp_region1_bytes(K, hidden)));
   return gs::launch_check("maxpool_pack_kernel");
 }
 
 
 // bf16 table [n_rows, K] (row pitch in elements) as a 2-D tensor map for tile::gather4: box = one K-block segment
 // (32 columns = 64 bytes) of ONE row - the instruction names four rows -, SWIZZLE_64B to match the UMMA stage layout
-static int32_t make_table_tensor_map(CUtensorMap* out, const void* table, int64_t n_rows, int32_t K, int64_t pitch) {
+static int32_t make_table_tensor_map(CUtensorMap* out, const void* table, int64_t n_rows, int32_t K, int64_t pitch,
+                                     int box_cols = gs::MP_KCOLS) {
   typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -695,10 +1659,11 @@ static int32_t make_table_tensor_map(CUtensorMap* out, const void* table, int64_
   }
   const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)n_rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)pitch * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)gs::MP_KCOLS, 1};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, 1};   // one K-block segment of ONE row; the instruction names four rows
   const cuuint32_t estride[2] = {1, 1};
   const CUresult rc = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(table), gdim, gstride, box, estride,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) {
     gs::set_error("cuTensorMapEncodeTiled failed (CUresult %d) for table [%lld, %d] pitch %lld", (int)rc, (long long)n_rows, K,
@@ -718,8 +1683,13 @@ static int32_t pool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K,
   GS_REQUIRE((pitch * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(table_bf16) & 15u) == 0,
              "gs_maxpool_mlp_fused: table rows must be 16-byte multiples and 16-byte aligned (pitch %% 8 == 0)");
   GS_REQUIRE((reinterpret_cast<uintptr_t>(packed_weights) & 127u) == 0, "gs_maxpool_mlp_fused: packed weights misaligned");
-  if (k > 128 || (K + gs::MP_KCOLS - 1) / gs::MP_KCOLS > gs::MP_MAX_KB || hidden % 128 != 0) {
-    gs::set_error("gs_maxpool_mlp_fused: needs k <= 128, K <= %d, hidden %% 128 == 0 (k=%d K=%d hidden=%d)",
+  // k4_kernel: 0 = tmem form (weights in tensor memory, 12+ operand stages; default); 3 = wide form, weights resident in
+  //            shared memory, 128-row tiles (k4_wide_producer: 1 TMA gather4, 0 cp.async); 2 = wide form, 256-row tiles;
+  //            1 = round-1 form (gathered rows = A operand, shared-memory transpose in the epilogue)
+  const int kernel_sel = gs::tuning("k4_kernel", 0);
+  const int tile_rows = kernel_sel == 2 ? 256 : kernel_sel == 0 ? (gs::tuning("k4_tile", 128) == 256 ? 256 : 128) : 128;
+  if (k > tile_rows || (K + gs::MP_KCOLS - 1) / gs::MP_KCOLS > gs::MP_MAX_KB || hidden % 128 != 0) {
+    gs::set_error("gs_maxpool_mlp_fused: needs k <= %d, K <= %d, hidden %% 128 == 0 (k=%d K=%d hidden=%d)", tile_rows,
                   gs::MP_MAX_KB * gs::MP_KCOLS, k, K, hidden);
     return GS_ERR_UNSUPPORTED;
   }
@@ -728,12 +1698,79 @@ static int32_t pool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K,
   memset(&prm, 0, sizeof(prm));
   prm.table = (const __nv_bfloat16*)table_bf16;
   prm.n_rows = n_rows; prm.pitch = pitch; prm.K = K; prm.kblocks = (K + gs::MP_KCOLS - 1) / gs::MP_KCOLS;
-  prm.row_ids = row_ids; prm.row0 = row0; prm.n_groups = n_groups; prm.k = k; prm.G = 128 / k;
+  prm.row_ids = row_ids; prm.row0 = row0; prm.n_groups = n_groups; prm.k = k; prm.G = tile_rows / k;
   prm.n_tiles = (n_groups + prm.G - 1) / prm.G;
   prm.hidden = hidden; prm.n_slices = hidden / 128;
   prm.wimg = (const unsigned char*)packed_weights; prm.bias = bias; prm.out = out; prm.ldo = ldo;
   prm.pool_mean = pool_mean;
   prm.issue_elect = gs::tuning("mma_issue", 1) != 0;
+  if (kernel_sel == 0) {
+    const unsigned char* ws = (const unsigned char*)packed_weights;
+    const int nt = tile_rows;                         // 256 (default) or 128 (k4_tile = 128)
+    prm.kblocks = (K + 63) / 64;
+    prm.G = nt / k;
+    prm.n_tiles = (n_groups + prm.G - 1) / prm.G;
+    prm.kb_t = prm.kblocks < gs::MPT_MAX_KB_T ? prm.kblocks : gs::MPT_MAX_KB_T;
+    prm.n_stages = (gs::MPW_SMEM_BYTES - (prm.kblocks - prm.kb_t) * gs::MPT_IMG) / (nt * 128);
+    if (prm.n_stages > gs::MPT_MAX_STAGES) prm.n_stages = gs::MPT_MAX_STAGES;
+    const int lim = gs::tuning("k4_stages", 0);
+    if (lim >= 4 && lim < prm.n_stages) prm.n_stages = lim;
+    prm.wimg = ws + mp_region0_bytes(K, hidden);
+    prm.wrows = (const uint32_t*)(ws + mp_region0_bytes(K, hidden) + mp_region1_bytes(K, hidden));
+    const void* fn = nt == 256 ? (const void*)gs::maxpool_mlp_tmem_kernel<256> : (const void*)gs::maxpool_mlp_tmem_kernel<128>;
+    const int32_t rc_attr = gs::ensure_dyn_smem(fn, gs::MPW_SMEM);
+    if (rc_attr != GS_OK) return rc_attr;
+    int64_t ctas_t = (int64_t)(gs::sm_count() / prm.n_slices) * prm.n_slices;   // a whole number of slice groups
+    if (ctas_t < prm.n_slices) ctas_t = prm.n_slices;
+    if (ctas_t > prm.n_tiles * prm.n_slices) ctas_t = prm.n_tiles * prm.n_slices;
+    if (nt == 128 && gs::tuning("k4_pipes", 1) == 2 && prm.n_stages >= 4) {
+      prm.n_stages &= ~1;                               // two half rings
+      const int32_t rc2 = gs::ensure_dyn_smem((const void*)gs::maxpool_mlp_tmem2_kernel, gs::MPW_SMEM);
+      if (rc2 != GS_OK) return rc2;
+      gs::maxpool_mlp_tmem2_kernel<<<(unsigned)ctas_t, gs::MPT_THREADS, gs::MPW_SMEM, (cudaStream_t)stream>>>(prm);
+      return gs::launch_check("maxpool_mlp_tmem2_kernel");
+    }
+    if (nt == 256)
+      gs::maxpool_mlp_tmem_kernel<256><<<(unsigned)ctas_t, gs::MPT_THREADS, gs::MPW_SMEM, (cudaStream_t)stream>>>(prm);
+    else
+      gs::maxpool_mlp_tmem_kernel<128><<<(unsigned)ctas_t, gs::MPT_THREADS, gs::MPW_SMEM, (cudaStream_t)stream>>>(prm);
+    return gs::launch_check("maxpool_mlp_tmem_kernel");
+  }
+  if (kernel_sel != 1) {
+    const int KC = kernel_sel == 3 ? 64 : 32;
+    const int prod = kernel_sel == 3 ? gs::tuning("k4_wide_producer", 1) : 0;     // 1: TMA gather4 (default), 0: cp.async
+    prm.kblocks = (K + KC - 1) / KC;
+    prm.G = tile_rows / k;
+    prm.n_tiles = (n_groups + prm.G - 1) / prm.G;
+    const int w_img = 128 * KC * 2, x_img = tile_rows * KC * 2;
+    prm.n_stages = (gs::MPW_SMEM_BYTES - prm.kblocks * w_img) / x_img;
+    if (prm.n_stages > gs::MPW_MAX_STAGES) prm.n_stages = gs::MPW_MAX_STAGES;
+    if (prod == 1) prm.n_stages = 4;                  // one producer warp per ring slot
+    if (prm.n_stages < 4) {
+      gs::set_error("gs_maxpool_mlp_fused: K=%d leaves %d operand stages (needs 4)", K, prm.n_stages);
+      return GS_ERR_UNSUPPORTED;
+    }
+    prm.dbg = gs::tuning("k4_dbg", 0);
+    if (kernel_sel == 3) prm.wimg += mp_region0_bytes(K, hidden);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (prod == 1) {
+      const int32_t rc = make_table_tensor_map(&tmap, table_bf16, n_rows, K, pitch, 64);
+      if (rc != GS_OK) return rc;
+    }
+    const void* fn = kernel_sel == 2 ? (const void*)gs::maxpool_mlp_wide_kernel<32, 256, 0>
+                     : prod == 1     ? (const void*)gs::maxpool_mlp_wide_kernel<64, 128, 1>
+                                     : (const void*)gs::maxpool_mlp_wide_kernel<64, 128, 0>;
+    const int32_t rc_attr = gs::ensure_dyn_smem(fn, gs::MPW_SMEM);
+    if (rc_attr != GS_OK) return rc_attr;
+    int64_t ctas_w = (int64_t)(gs::sm_count() / prm.n_slices) * prm.n_slices;   // a whole number of slice groups
+    if (ctas_w < prm.n_slices) ctas_w = prm.n_slices;
+    if (ctas_w > prm.n_tiles * prm.n_slices) ctas_w = prm.n_tiles * prm.n_slices;
+    const int threads = prod == 1 ? (4 + 6) * 32 : (8 + 6) * 32;
+    void* args[2] = {(void*)&prm, (void*)&tmap};
+    GS_CUDA(cudaLaunchKernel(fn, dim3((unsigned)ctas_w), dim3((unsigned)threads), args, gs::MPW_SMEM, (cudaStream_t)stream));
+    return gs::launch_check("maxpool_mlp_wide_kernel");
+  }
   {
     int32_t rc_attr = gs::ensure_dyn_smem((const void*)gs::maxpool_mlp_kernel<7, 5>, gs::MP_SMEM);
     if (rc_attr == GS_OK) rc_attr = gs::ensure_dyn_smem((const void*)gs::maxpool_mlp_kernel<6, 4>, gs::MP_SMEM);

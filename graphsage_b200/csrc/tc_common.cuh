@@ -102,6 +102,51 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr)
       : "memory");
 }
+// narrower TMEM loads (same 32x32b shape: thread t receives lane base + t): N consecutive fp32 columns from `taddr`
+#define GS_TMEM_LD_N(NAME, XN, NREG, OUTS, INIDX)                                                            \
+  __device__ __forceinline__ void NAME(uint32_t taddr, uint32_t (&r)[NREG]) {                                 \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b." XN ".b32 " OUTS ", [%" INIDX "];" : GS_TMEM_OUT_##NREG(r) : "r"(taddr) : "memory"); \
+  }
+#define GS_TMEM_OUT_1(r) "=r"(r[0])
+#define GS_TMEM_OUT_2(r) "=r"(r[0]), "=r"(r[1])
+#define GS_TMEM_OUT_4(r) "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+#define GS_TMEM_OUT_8(r) GS_TMEM_OUT_4(r), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+#define GS_TMEM_OUT_16(r) GS_TMEM_OUT_8(r), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+GS_TMEM_LD_N(tmem_ld_32x1, "x1", 1, "{%0}", "1")
+GS_TMEM_LD_N(tmem_ld_32x2, "x2", 2, "{%0,%1}", "2")
+GS_TMEM_LD_N(tmem_ld_32x4, "x4", 4, "{%0,%1,%2,%3}", "4")
+GS_TMEM_LD_N(tmem_ld_32x8, "x8", 8, "{%0,%1,%2,%3,%4,%5,%6,%7}", "8")
+GS_TMEM_LD_N(tmem_ld_32x16, "x16", 16, "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}", "16")
+// A operand from tensor memory (TS form): D[tmem] (+)= A[tmem] * B[smem desc]; whole warp executes, elect.sync on the instruction
+__device__ __forceinline__ void umma_ts_elect_bf16(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// registers -> TMEM, 32x32b shape: thread t of the warp writes lane (lane base + t), 32 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// mbarrier wait whose loop condition is a warp vote: the compiler then knows control flow stays warp-uniform after the
+// wait and keeps descriptors / addresses of the following tcgen05 instructions in uniform registers
+__device__ __forceinline__ void mbar_wait_uniform(uint64_t* bar, uint32_t parity) {
+  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+  }
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
@@ -139,6 +184,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }

@@ -55,6 +55,14 @@ for flag in (1, 0):
     t = timeit(lambda: ops.maxpool_mlp_fused(table[:, :F], B * 10, 25, Wm, bm, pk, row_ids=ids), n=20)
     print("mma_issue=%d  K4 maxpool hop2 (B=512, hidden 512): %.1f us  %.1f TFLOP/s" % (flag, t, 2.0 * B * 250 * F * H / t / 1e6), flush=True)
 lib.gs_set_tuning(b"mma_issue", 1)
+for ksel in (0, 1):
+    lib.gs_set_tuning(b"k4_kernel", ksel)
+    t = timeit(lambda: ops.maxpool_mlp_fused(table[:, :F], B * 10, 25, Wm, bm, pk, row_ids=ids), n=20)
+    print("k4_kernel=%d (0 wide / 1 round-1)  K4 maxpool hop2: %.1f us  %.1f TFLOP/s" % (ksel, t, 2.0 * B * 250 * F * H / t / 1e6), flush=True)
+    ids1 = ids[:B * 10]
+    t = timeit(lambda: ops.maxpool_mlp_fused(table[:, :F], B, 10, Wm, bm, pk, row_ids=ids1), n=20)
+    print("k4_kernel=%d  K4 maxpool hop1 (512 groups of 10): %.1f us" % (ksel, t), flush=True)
+lib.gs_set_tuning(b"k4_kernel", 1)
 
 if os.environ.get("TC_CHECK_G4", "0") == "1":
     # experimental K4 producers (1: TMA gather4, 2: + cluster multicast; hidden 128 has one slice, so 2 falls back to 1):
@@ -78,3 +86,4 @@ if os.environ.get("TC_CHECK_G4", "0") == "1":
         t = timeit(lambda: ops.maxpool_mlp_fused(table[:, :F], B * 10, 25, Wm, bm, pk, row_ids=ids), n=20)
         print("k4_producer=%d  K4 maxpool hop2: %.1f us  %.1f TFLOP/s" % (flag, t, 2.0 * B * 250 * F * H / t / 1e6), flush=True)
     lib.gs_set_tuning(b"k4_producer", 0)
+lib.gs_set_tuning(b"k4_kernel", 0)
