@@ -88,13 +88,14 @@ def build_graph(rank=0, world=1, barrier=None):
         np.save(base + "_adj.npy", g["adj"])
         np.save(base + "_feat.npy", g["features"])
         np.save(base + "_comm.npy", g["comm"])
+        np.save(base + "_deg.npy", g["deg"])
     barrier()
     if rank != 0:
         g = dict(adj=np.load(base + "_adj.npy"), features=np.load(base + "_feat.npy"), comm=np.load(base + "_comm.npy"),
-                 n=N_NODES, f=F, max_degree=MAX_DEG)
+                 deg=np.load(base + "_deg.npy"), n=N_NODES, f=F, max_degree=MAX_DEG)
     barrier()
     if rank == 0:
-        for suffix in ("_adj.npy", "_feat.npy", "_comm.npy"):
+        for suffix in ("_adj.npy", "_feat.npy", "_comm.npy", "_deg.npy"):
             os.remove(base + suffix)
     return g
 
@@ -176,6 +177,11 @@ def main():
     ap.add_argument("--repeats", type=int, default=0,
                     help="how many times each K-step timed region is repeated (median reported); 0 = auto (~0.3 s per leg)")
     ap.add_argument("--no-config3", action="store_true", help="skip the short max-pool/bf16 pass behind roofline_tensor")
+    ap.add_argument("--workload", default="reddit", choices=["reddit", "unsup", "rmat"],
+                    help="reddit = BASELINE configs[1] (default; the contract line); unsup = configs[3]: unsupervised training "
+                         "step, node-partitioned, data parallel; rmat = configs[4]: R-MAT graph, CSR sampler, partitioned")
+    ap.add_argument("--rmat-scale", type=int, default=20, help="log2 of the R-MAT id space (27 = BASELINE configs[4])")
+    ap.add_argument("--rmat-nodes", type=int, default=0, help="nodes after trimming (0 = 2^scale; 100000000 for configs[4])")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -218,8 +224,14 @@ def main():
     import graphsage_b200 as gs
     from graphsage_b200 import ops
 
-    g = build_graph(rank, world, (lambda: dist.barrier()) if dist is not None else None)
     dev = torch.device("cuda", local_rank)
+    if args.workload == "rmat":
+        import bench_extra
+        return bench_extra.run_rmat(args, rank, world, local_rank, dist, dev)
+    g = build_graph(rank, world, (lambda: dist.barrier()) if dist is not None else None)
+    if args.workload == "unsup":
+        import bench_extra
+        return bench_extra.run_unsup(args, g, rank, world, local_rank, dist, dev)
     tdtype = torch.bfloat16 if kind == "maxpool" else torch.float32
     table = torch.zeros((N_NODES + 1, ops.pad_cols(F)), dtype=tdtype, device=dev)
     table[:, :F] = torch.from_numpy(g["features"]).to(dev).to(tdtype)
@@ -436,32 +448,41 @@ def main():
         from graphsage_b200 import parallel
         bounds = parallel.community_bounds(g["comm"], world)      # cuts moved to community starts: no community straddles
         lo, hi = bounds[rank], bounds[rank + 1]
+        def run_partitioned(cache_rows, full):
+            hot = parallel.hot_remote_rows(g["adj"], N_NODES, world, rank, cache_rows, row_start=bounds)
+            shard = parallel.ShardedFeatures(g["features"][lo:hi], N_NODES, row_start=bounds, replica_ids=hot,
+                                             replica_rows=g["features"][hot])
+            model_p, infos_p = build_model(kind, shard, args.math)
+            pr = measure(model_p, lo, hi, "partitioned", probe_of(kind), do_e2e=full, reps=R if full else max(1, min(R, 5)))
+            rs = np.random.RandomState(1000 + rank)
+            smp, _ = model_p.sample(torch.from_numpy(rs.randint(lo, hi, size=BATCH).astype(np.int32)).to(dev), infos_p)
+            allids = torch.cat(smp)
+            rho_part = max_over_ranks(shard.remote_fraction(allids, use_replicas=False))
+            rho = max_over_ranks(shard.remote_fraction(allids))
+            out = {"value": pr["value"], "unit": "nodes/s", "ms_per_step": pr["ms_total"] / args.steps,
+                   "remote_row_fraction_by_partition": rho_part, "remote_row_fraction_after_replicas": rho,
+                   "replica_rows_per_gpu": int(len(hot)), "replica_fraction_of_table": float(len(hot)) / N_NODES,
+                   "gather_kernel_ms": pr["gather_kernel_ms"],
+                   "nvlink_GBps_per_gpu": rho * GATHER_BYTES / (pr["gather_kernel_ms"] * 1e-3) / 1e9,
+                   "nvlink_peak_GBps": 770.0}
+            if full:
+                out.update({"e2e": pr["e2e"], "e2e_ms_per_step": pr["ms_e2e"] / args.steps, "value_spread_ms": pr["ms_value"],
+                            "clocks": pr["clocks"], "launches": pr["launches"],
+                            "partition": "community-aligned contiguous ranges, %d..%d rows per GPU" % (
+                                min(np.diff(bounds)), max(np.diff(bounds))),
+                            "note": "node-partitioned features (contiguous community-aligned ranges), adjacency replicated, "
+                                    "remote rows pulled by the gather kernel over NVLink peer mappings (one bulk copy per row), "
+                                    "the hottest remote rows replicated locally (budget: 1/8 of the table per GPU unless "
+                                    "GS_HALO_CACHE_ROWS says otherwise); owner-computes seeds"})
+            barrier()
+            shard.close()
+            return out
+
         cache_rows = int(os.environ.get("GS_HALO_CACHE_ROWS", str(parallel.default_cache_rows(N_NODES, world))))
-        hot = parallel.hot_remote_rows(g["adj"], N_NODES, world, rank, cache_rows, row_start=bounds)
-        shard = parallel.ShardedFeatures(g["features"][lo:hi], N_NODES, row_start=bounds, replica_ids=hot,
-                                         replica_rows=g["features"][hot])
-        model_p, infos_p = build_model(kind, shard, args.math)
-        pr = measure(model_p, lo, hi, "partitioned", probe_of(kind))
-        rs = np.random.RandomState(1000 + rank)
-        smp, _ = model_p.sample(torch.from_numpy(rs.randint(lo, hi, size=BATCH).astype(np.int32)).to(dev), infos_p)
-        allids = torch.cat(smp)
-        rho_part = max_over_ranks(shard.remote_fraction(allids, use_replicas=False))
-        rho = max_over_ranks(shard.remote_fraction(allids))
-        part = {"value": pr["value"], "unit": "nodes/s", "ms_per_step": pr["ms_total"] / args.steps,
-                "e2e": pr["e2e"], "e2e_ms_per_step": pr["ms_e2e"] / args.steps,
-                "remote_row_fraction_by_partition": rho_part, "remote_row_fraction_after_replicas": rho,
-                "replica_rows_per_gpu": int(len(hot)), "replica_fraction_of_table": float(len(hot)) / N_NODES,
-                "partition": "community-aligned contiguous ranges, %d..%d rows per GPU" % (
-                    min(np.diff(bounds)), max(np.diff(bounds))),
-                "gather_kernel_ms": pr["gather_kernel_ms"],
-                "nvlink_GBps_per_gpu": rho * GATHER_BYTES / (pr["gather_kernel_ms"] * 1e-3) / 1e9,
-                "nvlink_peak_GBps": 770.0, "value_spread_ms": pr["ms_value"], "clocks": pr["clocks"],
-                "launches": pr["launches"],
-                "note": "node-partitioned features (contiguous community-aligned ranges), adjacency replicated, "
-                        "remote rows pulled by the gather kernel over NVLink peer mappings (bulk copies), the hottest "
-                        "remote rows (by in-table frequency) replicated locally; owner-computes seeds"}
-        barrier()
-        shard.close()
+        part = run_partitioned(cache_rows, True)
+        sweep = os.environ.get("GS_HALO_CACHE_SWEEP", "")
+        if sweep:
+            part["replica_sweep"] = [run_partitioned(int(float(f) * N_NODES), False) for f in sweep.split(",") if f.strip()]
 
     # config 3 (BASELINE configs[2]) in the same run: max-pool aggregator over a bf16 table, K4 on tcgen05
     c3 = None

@@ -216,10 +216,15 @@ struct ShardTab {
 struct ShardRows {
   ShardTab t;
   int64_t pitch;
+  int32_t locators;           // the id lists were translated by gs_translate_ids: >= 0 local row index, < 0 -> -(global id) - 1
   __device__ __forceinline__ const float* row(int64_t id) const {
     const float* mine = t.base[t.my_shard];
-    if (id < 0 || id >= t.n_global_rows - 1) return mine + t.zero_row * pitch;
-    if (t.remap) {
+    if (locators) {
+      if (id >= 0) return mine + id * pitch;
+      id = -id - 1;                                  // a remote row: owner found below
+    } else if (id < 0 || id >= t.n_global_rows - 1) {
+      return mine + t.zero_row * pitch;
+    } else if (t.remap) {
       const int32_t s = __ldg(t.remap + id);
       if (s >= 0) return mine + (int64_t)s * pitch;
     } else if (id >= t.row_start[t.my_shard] && id < t.row_start[t.my_shard + 1]) {
@@ -472,6 +477,24 @@ __global__ void __launch_bounds__(256) l2_normalize_kernel(float* __restrict__ x
 // shard table (peer-mapped pointers).  Remote rows travel over NVLink as 128-bit loads issued by
 // the consuming kernel itself - the halo exchange IS the gather.
 // ------------------------------------------------------------------------------------------
+// ids -> locators for a node-partitioned table with replicas: loc = remap[id] (row index inside this GPU's own buffer) when
+// the row is held locally - own rows, replicas, and the zero row for ids outside [0, N) -, else -(id) - 1.  One thread per id:
+// the dependent 4-byte lookup leaves the gather kernel's copy-issue path (where it cost 8 us per step).
+__global__ void __launch_bounds__(256) translate_ids_kernel(const int32_t* __restrict__ remap, int64_t n_global_rows,
+                                                            int32_t zero_row, const int32_t* __restrict__ ids, int64_t n,
+                                                            int32_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t id = ids[i];
+    int32_t loc;
+    if (id < 0 || id >= n_global_rows - 1) loc = zero_row;
+    else {
+      loc = __ldg(remap + id);
+      if (loc < 0) loc = -id - 1;
+    }
+    out[i] = loc;
+  }
+}
+
 template <int kUnroll>
 __global__ void __launch_bounds__(256) gather_mean_sharded_kernel(const __grid_constant__ ShardRows st, int F,
                                                                   const __grid_constant__ SegTable tab, int include_self,
@@ -760,15 +783,30 @@ static int32_t fill_shard_tab(const gs_sharded_table* t, gs::ShardRows& sr, int6
 
 extern "C" {
 
+int32_t gs_translate_ids(const gs_sharded_table* table_host, const int32_t* ids, int64_t n, int32_t* out, void* stream) {
+  GS_REQUIRE(table_host && table_host->remap, "gs_translate_ids: the table has no remap (no replicas)");
+  GS_REQUIRE(n >= 0, "gs_translate_ids: n < 0");
+  if (n == 0) return GS_OK;
+  GS_REQUIRE(ids && out, "gs_translate_ids: NULL pointer");
+  GS_REQUIRE(table_host->zero_row >= 0 && table_host->zero_row < 0x7fffffffLL, "gs_translate_ids: zero_row out of range");
+  int64_t blocks = (n + 255) / 256;
+  int64_t cap = (int64_t)gs::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  gs::translate_ids_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(table_host->remap, table_host->n_global_rows,
+                                                                                (int32_t)table_host->zero_row, ids, n, out);
+  return gs::launch_check("translate_ids_kernel");
+}
+
 int32_t gs_gather_mean_sharded(const gs_sharded_table* table_host, int32_t dtype, int32_t F, int64_t pitch,
-                               const gs_segment* segments_host, int32_t n_segments, int32_t include_self, void* out_self,
-                               void* out_mean, int64_t out_pitch, void* stream) {
+                               const gs_segment* segments_host, int32_t n_segments, int32_t include_self,
+                               int32_t ids_are_locators, void* out_self, void* out_mean, int64_t out_pitch, void* stream) {
   GS_REQUIRE(dtype == GS_F32, "gs_gather_mean_sharded: only GS_F32 (dtype=%d)", dtype);
   GS_REQUIRE(n_segments >= 0 && n_segments <= GS_MAX_SEGMENTS && (segments_host || n_segments == 0),
              "gs_gather_mean_sharded: bad segments");
   gs::ShardRows sr;
   int32_t rc = fill_shard_tab(table_host, sr, pitch, "gs_gather_mean_sharded");
   if (rc != GS_OK) return rc;
+  sr.locators = ids_are_locators ? 1 : 0;
   gs::SegTable tab;
   memset(&tab, 0, sizeof(tab));
   tab.n_segments = n_segments;

@@ -249,6 +249,16 @@ def gather_mean(src, segments, include_self=False, want_self=True, out_pitch=Non
     return (out_self if want_self else None), out_mean
 
 
+def translate_ids(table, ids):
+    """ids -> locators of a parallel.ShardedFeatures with replicas (gs_translate_ids): >= 0 a row of this GPU's own buffer,
+    < 0 -> -(global id) - 1 (the row has to come from its owner)."""
+    ids = _i32(ids.reshape(-1), "ids")
+    out = torch.empty_like(ids)
+    check(lib().gs_translate_ids(table.c_table(), ptr(ids), ids.numel(), ptr(out), stream_ptr()))
+    _launched(1 if ids.numel() else 0)
+    return out
+
+
 def _gather_mean_sharded(src, segments, include_self, want_self, out_pitch, out_mean, out_self):
     F = src.shape[1]
     if out_pitch is None:
@@ -258,10 +268,29 @@ def _gather_mean_sharded(src, segments, include_self, want_self, out_pitch, out_
         out_mean = torch.empty((rows, out_pitch), dtype=torch.float32, device=src.device)
     if want_self and out_self is None:
         out_self = torch.empty((rows, out_pitch), dtype=torch.float32, device=src.device)
+    locators = 0
+    if getattr(src, "remap", None) is not None and any(s.self_ids is not None or s.neigh_ids is not None for s in segments):
+        # replicas: resolve every id list once (one pass per distinct tensor; hop-1 ids are self ids of one segment and
+        # neighbour ids of another) so the gather kernel's issue path has no table lookup
+        done, segs = {}, []
+
+        def tr(t):
+            if t is None:
+                return None
+            key = (t.data_ptr(), t.numel())
+            if key not in done:
+                done[key] = translate_ids(src, t)
+            return done[key]
+
+        for s in segments:
+            if (s.self_ids is None) != (s.neigh_ids is None):
+                raise ValueError("a segment over a replicated sharded table must address self and neighbours the same way")
+            segs.append(Seg(s.n, s.k, tr(s.self_ids), tr(s.neigh_ids), s.self_row0, s.neigh_row0, s.out_row0))
+        segments, locators = segs, 1
     arr = (Segment * max(len(segments), 1))(*[s.c_struct() for s in segments])
     ev = _probe("gather_mean/%d" % rows)
     check(lib().gs_gather_mean_sharded(src.c_table(), _lib.GS_F32, F, src.pitch, arr, len(segments),
-                                       int(bool(include_self)), ptr(out_self) if want_self else 0, ptr(out_mean),
+                                       int(bool(include_self)), locators, ptr(out_self) if want_self else 0, ptr(out_mean),
                                        out_pitch, stream_ptr()))
     _launched(1 if rows else 0, ev)
     return (out_self if want_self else None), out_mean

@@ -58,9 +58,9 @@ def owner_of(ids, n_nodes, world, row_start=None):
 
 
 def default_cache_rows(n_nodes, world):
-    """Replica budget used by bench.py when none is given: as many rows as one shard (each GPU then stores 2/world
-    of the table)."""
-    return rows_per_shard(n_nodes, world) if world > 1 else 0
+    """Replica budget used by bench.py when none is given: one eighth of the table per GPU, whatever the GPU count
+    (at 8 GPUs a GPU then holds its own eighth plus as many replica rows)."""
+    return (int(n_nodes) + 7) // 8 if world > 1 else 0
 
 
 def hot_remote_rows(adj, n_nodes, world, rank, n_rows, row_start=None):
@@ -124,6 +124,65 @@ def route_seeds(seeds, n_nodes, group=None, row_start=None):
     return out
 
 
+def hot_remote_rows_csr(indices, n_nodes, world, rank, n_rows, row_start=None, chunk=1 << 27):
+    """Replica choice for a graph held as CSR on the device (no padded table): the `n_rows` remote nodes with the highest
+    in-degree - under uniform neighbour sampling a node is read in proportion to how many adjacency lists contain it.
+    `indices` is the CSR column array (CUDA int32); returns sorted int64 ids on the host."""
+    if n_rows <= 0 or world <= 1:
+        return np.zeros(0, dtype=np.int64)
+    rs = uniform_bounds(n_nodes, world) if row_start is None else list(row_start)
+    lo, hi = rs[rank], rs[rank + 1]
+    cnt = torch.zeros((n_nodes,), dtype=torch.int64, device=indices.device)
+    for i in range(0, indices.numel(), chunk):
+        part = indices[i:i + chunk].long()
+        cnt += torch.bincount(part.clamp_(0, n_nodes - 1), minlength=n_nodes)
+        del part
+    cnt[lo:hi] = -1
+    n_rows = int(min(n_rows, n_nodes - (hi - lo)))
+    hot = torch.topk(cnt, n_rows, sorted=False).indices
+    hot = hot[cnt[hot] > 0]
+    return np.sort(hot.cpu().numpy()).astype(np.int64)
+
+
+def broadcast_parameters(params, src=0, group=None):
+    """Make every rank start from rank `src`'s weights (data-parallel training: the aggregator / head weights are
+    replicated, < 1 MB in total)."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    with torch.no_grad():
+        for p in params:
+            dist.broadcast(p.data, src=src, group=group)
+
+
+def allreduce_gradients(params, group=None):
+    """The ONE collective of the data-parallel training step ("one gradient all-reduce of < 1 MB"): the
+    gradients of all replicated weights are packed into a single buffer, summed over the ranks (NCCL all-reduce over
+    NVLink / gloo on CPU), divided by the world size - the mean over the global batch, since every rank's loss is a
+    mean over its own equally sized batch - and written back.  Parameters without a gradient contribute zeros so that
+    the buffer has the same layout on every rank.  Returns the number of bytes reduced."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    params = list(params)
+    if not params:
+        return 0
+    world = dist.get_world_size(group)
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).to(torch.float32) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(float(world))
+    off = 0
+    for p in params:
+        n = p.numel()
+        g = flat[off:off + n].view_as(p).to(p.dtype)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += n
+    return flat.numel() * 4
+
+
 class _CudaView(object):
     """Expose a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
 
@@ -143,7 +202,8 @@ class ShardedFeatures(object):
     supervised_train.py:133-135, local on every rank), then the replicas.
     """
 
-    def __init__(self, local_rows, n_nodes, group=None, device=None, row_start=None, replica_ids=None, replica_rows=None):
+    def __init__(self, local_rows, n_nodes, group=None, device=None, row_start=None, replica_ids=None, replica_rows=None,
+                 n_features=None):
         import torch.distributed as dist
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -154,16 +214,22 @@ class ShardedFeatures(object):
             raise ValueError("row_start must have world + 1 entries running from 0 to n_nodes")
         if self.world > _lib.MAX_SHARDS:
             raise ValueError("at most %d shards" % _lib.MAX_SHARDS)
-        local_rows = torch.as_tensor(local_rows, dtype=torch.float32)
-        F = local_rows.shape[1]
         lo, hi = self.row_start[self.rank], self.row_start[self.rank + 1]
         n_local = hi - lo
         self.lo, self.hi, self.n_local = lo, hi, n_local
-        if local_rows.shape[0] != n_local:
-            raise ValueError("rank %d must pass %d rows (got %d)" % (self.rank, n_local, local_rows.shape[0]))
+        if local_rows is None:
+            # big shards are produced on the device: the caller fills self.local[:n_local, :F] itself (then fill_replicas())
+            if not n_features:
+                raise ValueError("n_features is required when local_rows is None")
+            F = int(n_features)
+        else:
+            local_rows = torch.as_tensor(local_rows, dtype=torch.float32)
+            F = local_rows.shape[1]
+            if local_rows.shape[0] != n_local:
+                raise ValueError("rank %d must pass %d rows (got %d)" % (self.rank, n_local, local_rows.shape[0]))
         rep_ids = np.zeros(0, np.int64) if replica_ids is None else np.asarray(replica_ids, dtype=np.int64).reshape(-1)
         if len(rep_ids):
-            if replica_rows is None or len(replica_rows) != len(rep_ids):
+            if replica_rows is not None and len(replica_rows) != len(rep_ids):
                 raise ValueError("replica_rows must hold one row per replica id")
             if (np.diff(rep_ids) <= 0).any() or rep_ids[0] < 0 or rep_ids[-1] >= self.n_nodes \
                     or ((rep_ids >= lo) & (rep_ids < hi)).any():
@@ -179,16 +245,21 @@ class ShardedFeatures(object):
         self._own_ptr = p.value
         self.local = torch.as_tensor(_CudaView(p.value, (rows_total, self.pitch)), device=self.device)
         self.local.zero_()
-        self.local[:n_local, :F] = local_rows.to(self.device)
+        if local_rows is not None:
+            self.local[:n_local, :F] = local_rows.to(self.device)
         self.zero_row = n_local
-        self.remap = None
+        self.remap, self._pending_remap = None, None
         if len(rep_ids):
-            self.local[n_local + 1:, :F] = torch.as_tensor(replica_rows, dtype=torch.float32).to(self.device)
-            remap = np.full(self.n_nodes + 1, -1, dtype=np.int32)
-            remap[lo:hi] = np.arange(n_local, dtype=np.int32)
+            rid = torch.from_numpy(rep_ids).to(self.device)
+            remap = torch.full((self.n_nodes + 1,), -1, dtype=torch.int32, device=self.device)
+            remap[lo:hi] = torch.arange(n_local, dtype=torch.int32, device=self.device)
             remap[self.n_nodes] = n_local
-            remap[rep_ids] = n_local + 1 + np.arange(len(rep_ids), dtype=np.int32)
-            self.remap = torch.from_numpy(remap).to(self.device)
+            remap[rid] = n_local + 1 + torch.arange(len(rep_ids), dtype=torch.int32, device=self.device)
+            if replica_rows is not None:
+                self.local[n_local + 1:, :F] = torch.as_tensor(replica_rows, dtype=torch.float32).to(self.device)
+                self.remap = remap
+            else:
+                self._pending_remap = remap                  # installed by fill_replicas() once the owners' rows exist
         torch.cuda.synchronize()
         # exchange IPC handles
         handle = ctypes.create_string_buffer(64)
@@ -220,6 +291,26 @@ class ShardedFeatures(object):
 
     def c_table(self):
         return ctypes.byref(self._table)
+
+    def fill_replicas(self, chunk=1 << 20):
+        """Copy the replica rows from their owners (peer loads over NVLink) after EVERY rank has filled its own rows;
+        collective (barriers).  Only needed when the shard was built with replica_ids but without replica_rows."""
+        import torch.distributed as dist
+        from . import ops
+        torch.cuda.synchronize()
+        if self.world > 1 and dist.is_initialized():
+            dist.barrier(group=self.group)                    # every owner's rows are in place
+        if self._pending_remap is not None:
+            ids = torch.from_numpy(self.replica_ids.astype(np.int32)).to(self.device)
+            base = self.n_local + 1
+            for i in range(0, ids.numel(), chunk):
+                part = ids[i:i + chunk]
+                ops.gather_rows(self, part, out=self.local[base + i:base + i + part.numel(), :self.shape[1]])
+            torch.cuda.synchronize()
+            self.remap, self._pending_remap = self._pending_remap, None
+            self._table.remap = self.remap.data_ptr()
+        if self.world > 1 and dist.is_initialized():
+            dist.barrier(group=self.group)
 
     def remote_fraction(self, ids, use_replicas=True):
         """Fraction of the given global ids whose feature row must come over NVLink (not owned; with use_replicas,

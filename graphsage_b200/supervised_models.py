@@ -256,7 +256,7 @@ class SupervisedGraphsage(SampleAndAggregate):
 
     def __init__(self, num_classes, placeholders, features, adj, degrees, layer_infos, concat=True,
                  aggregator_type="mean", model_size="small", sigmoid_loss=False, identity_dim=0, learning_rate=0.01,
-                 weight_decay=0.0, device="cuda", **kwargs):
+                 weight_decay=0.0, device="cuda", distributed=False, group=None, **kwargs):
         super(SupervisedGraphsage, self).__init__(placeholders, features, adj, degrees, layer_infos, concat=concat,
                                                   aggregator_type=aggregator_type, model_size=model_size,
                                                   identity_dim=identity_dim, device=device, **kwargs)
@@ -265,6 +265,7 @@ class SupervisedGraphsage(SampleAndAggregate):
         self.num_classes = num_classes
         self.sigmoid_loss = sigmoid_loss
         self.learning_rate, self.weight_decay = learning_rate, weight_decay
+        self.distributed, self.group, self.last_allreduce_bytes = bool(distributed), group, 0
         self.build()
 
     def build(self):
@@ -273,6 +274,9 @@ class SupervisedGraphsage(SampleAndAggregate):
         dim_mult = 2 if self.concat else 1
         self.node_pred_vars = {"weights": glorot([dim_mult * self.dims[-1], self.num_classes], device=self.device),
                                "bias": zeros([self.num_classes], device=self.device)}   # supervised_models.py:88-90
+        if self.distributed:                                                     # every rank starts from rank 0's weights
+            from .parallel import broadcast_parameters
+            broadcast_parameters(self.parameters(), 0, self.group)
         for p in self.parameters():
             p.requires_grad_(True)
         self.optimizer = torch.optim.Adam(self.parameters(), lr=self.learning_rate)      # TF AdamOptimizer defaults
@@ -304,6 +308,9 @@ class SupervisedGraphsage(SampleAndAggregate):
         self.optimizer.zero_grad(set_to_none=True)
         loss = self.loss(batch, labels)
         loss.backward()
+        if self.distributed:                                                     # data parallel: mean gradient over ranks
+            from .parallel import allreduce_gradients
+            self.last_allreduce_bytes = allreduce_gradients(self.parameters(), self.group)
         for p in self.parameters():                                              # clip_by_value(grad, -5, 5)  :93-94
             if p.grad is not None:
                 p.grad.clamp_(-5.0, 5.0)

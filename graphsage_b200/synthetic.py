@@ -94,3 +94,38 @@ def rmat_csr(scale, edge_factor=20, a=0.57, b=0.19, c=0.19, d=0.05, n_nodes=None
     rows, cols = key // n, (key % n).astype(np.int32)
     indptr = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=n))]).astype(np.int64)
     return indptr, cols
+
+
+def rmat_scramble_constants(n):
+    """(mul, mul_inv, add) of the node-id bijection y = (x * mul + add) mod n applied by the device generator (R-MAT puts
+    its hubs on ids with few set bits; contiguous-range partitions would otherwise give every hub to GPU 0)."""
+    import math
+    mul = 0x9E3779B1 % n
+    if mul < 2:
+        mul = 1
+    while math.gcd(mul, n) != 1:
+        mul += 1
+    return mul, pow(mul, -1, n), 0x7F4A7C15 % n
+
+
+def rmat_csr_device(scale, n_nodes=None, edge_factor=20.0, a=0.57, b=0.19, c=0.19, d=0.05, seed=123, device="cuda"):
+    """R-MAT graph written directly as CSR on the device (gs_rmat_degrees -> prefix sum -> gs_rmat_fill; contract in
+    csrc/rmat.cu / oracle/rmat.py).  Returns (indptr int64 [n+1], indices int32 [m]) CUDA tensors.  BASELINE configs[4]:
+    scale=27, n_nodes=100_000_000 (8 GB of indices)."""
+    import torch
+    from . import _lib
+    from ._lib import check, lib, ptr, stream_ptr
+    n = int(n_nodes) if n_nodes else 1 << scale
+    mul, mul_inv, add = rmat_scramble_constants(n)
+    dev = torch.device(device)
+    deg = torch.empty((n,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().gs_rmat_degrees(scale, n, float(edge_factor), a, b, c, d, seed & (2**64 - 1), mul, mul_inv, add, ptr(deg),
+                                    stream_ptr()))
+        indptr = torch.zeros((n + 1,), dtype=torch.int64, device=dev)
+        torch.cumsum(deg, dim=0, out=indptr[1:])
+        m = int(indptr[-1].item())
+        indices = torch.empty((m,), dtype=torch.int32, device=dev)
+        check(lib().gs_rmat_fill(scale, n, a, b, c, d, seed & (2**64 - 1), mul, mul_inv, add, ptr(indptr), ptr(indices),
+                                 stream_ptr()))
+    return indptr, indices

@@ -35,7 +35,7 @@ class UnsupervisedGraphsage(SampleAndAggregate):
 
     def __init__(self, placeholders, features, adj, degrees, layer_infos, concat=True, aggregator_type="mean",
                  model_size="small", identity_dim=0, neg_sample_size=20, neg_sample_weights=1.0, learning_rate=0.00001,
-                 weight_decay=0.0, seed=123, device="cuda", **kwargs):
+                 weight_decay=0.0, seed=123, device="cuda", distributed=False, group=None, **kwargs):
         super(UnsupervisedGraphsage, self).__init__(placeholders, features, adj, degrees, layer_infos, concat=concat,
                                                     aggregator_type=aggregator_type, model_size=model_size,
                                                     identity_dim=identity_dim, device=device, **kwargs)
@@ -49,6 +49,10 @@ class UnsupervisedGraphsage(SampleAndAggregate):
         self.link_pred_layer = BipartiteEdgePredLayer(dim_mult * self.dims[-1], dim_mult * self.dims[-1], placeholders,
                                                       neg_sample_weights=self.neg_sample_weights, bilinear_weights=False,
                                                       device=device, name="edge_predict")      # models.py:362-365
+        self.distributed, self.group, self.last_allreduce_bytes = bool(distributed), group, 0
+        if self.distributed:                                                         # every rank starts from rank 0's weights
+            from .parallel import broadcast_parameters
+            broadcast_parameters(self.parameters(), 0, group)
         for p in self.parameters():
             p.requires_grad_(True)
         self.optimizer = torch.optim.Adam(self.parameters(), lr=self.learning_rate)
@@ -87,6 +91,9 @@ class UnsupervisedGraphsage(SampleAndAggregate):
         self.optimizer.zero_grad(set_to_none=True)
         loss = self.loss(batch1, batch2)
         loss.backward()
+        if self.distributed:                                                         # data parallel: mean gradient over ranks
+            from .parallel import allreduce_gradients
+            self.last_allreduce_bytes = allreduce_gradients(self.parameters(), self.group)
         for p in self.parameters():
             if p.grad is not None:
                 p.grad.clamp_(-5.0, 5.0)                                             # models.py:380-381

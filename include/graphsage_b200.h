@@ -181,9 +181,15 @@ typedef struct {
   const int32_t* remap;                  /* device, [n_global_rows] or NULL (see above) */
 } gs_sharded_table;
 
+/* ids_are_locators != 0: the segments' id lists were translated by gs_translate_ids (below) */
 int32_t gs_gather_mean_sharded(const gs_sharded_table* table_host, int32_t dtype, int32_t F, int64_t pitch,
                                const gs_segment* segments_host, int32_t n_segments, int32_t include_self,
-                               void* out_self, void* out_mean, int64_t out_pitch, void* stream);
+                               int32_t ids_are_locators, void* out_self, void* out_mean, int64_t out_pitch,
+                               void* stream);
+/* ids -> locators for a table with replicas (remap != NULL): out[i] = remap[ids[i]] (a row index inside this GPU's own
+ * buffer) when the row is held locally - own rows, replicas, the zero row for ids outside [0, N) -, else -(ids[i]) - 1.
+ * One cheap, fully parallel pass per id list; the gather kernel then needs no table lookup on its copy-issue path. */
+int32_t gs_translate_ids(const gs_sharded_table* table_host, const int32_t* ids, int64_t n, int32_t* out, void* stream);
 int32_t gs_gather_rows_sharded(const gs_sharded_table* table_host, int32_t dtype, int32_t F, int64_t pitch,
                                const int32_t* ids, int64_t n, void* out, int64_t out_pitch, void* stream);
 
@@ -205,6 +211,19 @@ int32_t gs_gather_rows_f32(const void* feats, int32_t dtype, int64_t n_rows, int
  * bf16 source table of the max-pool path (the hidden[hop] list of models.py:321-329 kept in the K4 operand type). */
 int32_t gs_cast_rows_bf16(const float* x, int64_t n, int32_t F, int64_t ldx, void* out_bf16, int64_t out_pitch,
                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * R-MAT graph written directly as CSR on the device (BASELINE.json configs[4]: scale 27 trimmed to 10^8 nodes, about 20
+ * entries per node, a, b, c, d = 0.57, 0.19, 0.19, 0.05).  No reference counterpart - the reference reads graphs from
+ * disk (graphsage/utils.py:19-75); this is the synthetic stand-in at that size.  Contract: oracle/rmat.py, csrc/rmat.cu.
+ *   1. gs_rmat_degrees -> deg[n_nodes] (int32);  2. caller: indptr = exclusive prefix sum (int64 [n_nodes + 1]);
+ *   3. gs_rmat_fill -> indices[indptr[n_nodes]] (int32 neighbour ids, unsorted, duplicates possible, no self loops).
+ * Node ids are scrambled by y = (x * mul + add) mod n_nodes, which must be a bijection: (mul * mul_inv) mod n_nodes == 1.
+ * --------------------------------------------------------------------------------------------- */
+int32_t gs_rmat_degrees(int32_t scale, int64_t n_nodes, double edge_factor, double a, double b, double c, double d,
+                        uint64_t seed, uint64_t mul, uint64_t mul_inv, uint64_t add, int32_t* deg_out, void* stream);
+int32_t gs_rmat_fill(int32_t scale, int64_t n_nodes, double a, double b, double c, double d, uint64_t seed, uint64_t mul,
+                     uint64_t mul_inv, uint64_t add, const int64_t* indptr, int32_t* indices, void* stream);
 
 /* segmented max over fixed fanout: out[i, c] = max_j x[i*k + j, c]   (aggregators.py:182) */
 int32_t gs_segment_max(const float* x, int64_t n, int32_t k, int32_t C, int64_t ldx,

@@ -27,5 +27,6 @@ from .aggregate import (gather_rows, mean_aggregator, gcn_aggregator,
                         maxpool_aggregator, meanpool_aggregator, dense, l2_normalize, glorot_range,
                         sample_khop, aggregate_khop, forward_2hop)
 from .adjacency import construct_adj, construct_test_adj, build_padded_adj
+from . import rmat
 
 __all__ = [n for n in dir() if not n.startswith("_")]

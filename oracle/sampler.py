@@ -77,8 +77,11 @@ def sample_csr(indptr, indices, ids, k, seed, counter, replace_if_short=True, pa
     out = np.full((n, k), pad_id, dtype=np.int32)
     if n == 0 or k == 0:
         return out
-    start = indptr[ids]
-    deg = indptr[ids + 1] - start
+    n_nodes = len(indptr) - 1
+    valid = (ids >= 0) & (ids < n_nodes)              # ids outside [0, n_nodes) - the dummy id included - have no neighbours
+    safe = np.where(valid, ids, 0)
+    start = np.where(valid, indptr[safe], 0)
+    deg = np.where(valid, indptr[safe + 1] - indptr[safe], 0)
     r = _draws(seed, counter, k, c2=np.arange(n, dtype=np.uint32), tag=STREAM_CSR)  # [n, k]
     # --- with replacement rows
     short = (deg > 0) & (deg < k)

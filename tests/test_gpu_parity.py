@@ -775,3 +775,57 @@ def test_build_padded_adj_bit_exact(gs):
     # the table feeds the sampler directly
     out = gs.ops.sample_padded(adj, dev(np.arange(100, dtype=np.int32)), 10, 1, 1)
     assert out.shape == (100, 10)
+
+
+# ---------------------------------------------------------------- config 5 pieces: device R-MAT generator, CSR-sampled model
+@pytest.mark.parametrize("scale,n", [(13, 5000), (10, 1024), (12, 4095)])
+def test_rmat_generator_bit_exact(gs, scale, n):
+    from graphsage_b200.synthetic import rmat_csr_device
+    indptr, indices = rmat_csr_device(scale, n, 20.0, seed=11)
+    ref_ptr, ref_idx = oracle.rmat.rmat_csr(scale, n, 20.0, seed=11)
+    np.testing.assert_array_equal(indptr.cpu().numpy(), ref_ptr)
+    np.testing.assert_array_equal(indices.cpu().numpy(), ref_idx)
+
+
+def test_rmat_generator_properties_at_scale(gs):
+    """size-independent properties at a size the oracle would not finish quickly: 2^20 nodes, ~21 M entries"""
+    from graphsage_b200.synthetic import rmat_csr_device
+    n = 1 << 20
+    indptr, indices = rmat_csr_device(20, n, 20.0, seed=123)
+    deg = (indptr[1:] - indptr[:-1])
+    m = int(indptr[-1])
+    assert indices.numel() == m and abs(m / float(n) - 20.0) < 0.1
+    assert int(indices.min()) >= 0 and int(indices.max()) < n
+    rows = torch.repeat_interleave(torch.arange(n, device="cuda"), deg)
+    assert int((rows == indices.long()).sum()) == 0                         # no self loops
+    indeg = torch.bincount(indices.long(), minlength=n)
+    # b == c: the in-degree and out-degree distributions have the same heavy tail
+    assert 0.5 < float(indeg.max()) / float(deg.max()) < 2.0 and int(deg.max()) > 2000
+    # the hubs are scrambled over the id range, not packed at its start
+    top = torch.topk(deg, 64).indices
+    assert int((top < n // 8).sum()) < 32
+
+
+def test_csr_sampled_model_vs_oracle(gs):
+    """SampleAndAggregate over a CSRNeighborSampler (the config-5 path) against the oracle: per-node draws bit-exact
+    (oracle.sample_csr), outputs within 1e-4."""
+    rs = np.random.RandomState(17)
+    indptr, indices = oracle.rmat.rmat_csr(11, 2000, 12.0, seed=3)
+    n, f, B = 2000, 64, 96
+    feats = np.vstack([rs.randn(n, f).astype(np.float32), np.zeros((1, f), np.float32)])
+    seeds = rs.randint(0, n, size=B).astype(np.int32)
+    gs.set_default_math("fp32")
+    sampler = gs.CSRNeighborSampler(dev(indptr), dev(indices), seed=9)
+    infos = [gs.SAGEInfo("node", sampler, 25, 32), gs.SAGEInfo("node", sampler, 10, 32)]
+    m = gs.SampleAndAggregate({"batch_size": B, "dropout": 0.}, dev(feats), None, None, infos, concat=True,
+                              aggregator_type="mean")
+    out = m.forward(dev(seeds), normalize=True).cpu().numpy()
+    h1 = oracle.sample_csr(indptr, indices, seeds, 10, 9, 0, pad_id=n).reshape(-1)
+    h2 = oracle.sample_csr(indptr, indices, h1, 25, 9, 1, pad_id=n).reshape(-1)
+    sampler.counter = 0
+    got, support = m.sample(dev(seeds), infos)
+    np.testing.assert_array_equal(got[1].cpu().numpy(), h1)
+    np.testing.assert_array_equal(got[2].cpu().numpy(), h2)
+    aggs = [dict(type="mean", **{k: v.cpu().numpy() for k, v in a.vars.items()}) for a in m.aggregators]
+    ref = oracle.l2_normalize(oracle.aggregate_khop([seeds, h1, h2], feats, [25, 10], [1, 10, 250], B, aggs, True))
+    assert rel_err(out, ref) < TOL

@@ -125,3 +125,23 @@ def test_rmat_generator_properties():
     assert ip2.shape == (3001,) and ix2.max() < 3000
     und = set(zip(np.repeat(np.arange(3000), np.diff(ip2)).tolist(), ix2.tolist()))
     assert all((v, u) in und for (u, v) in list(und)[:2000])      # symmetric
+
+
+def test_rmat_oracle_properties():
+    """the R-MAT oracle (config 5's graph): mean degree = edge_factor, no self loops, ids in range, hubs scrambled, and the
+    row marginal it is built from: a node's expected degree follows (a+b)^zeros (c+d)^ones of its R-MAT id"""
+    import oracle
+    n = 1 << 12
+    indptr, indices = oracle.rmat.rmat_csr(12, n, 16.0, seed=5)
+    deg = np.diff(indptr)
+    assert abs(indptr[-1] / float(n) - 16.0) < 0.2
+    assert indices.min() >= 0 and indices.max() < n
+    assert not (np.repeat(np.arange(n), deg) == indices).any()
+    mul, mul_inv, add = oracle.rmat.scramble_constants(n)
+    assert (mul * mul_inv) % n == 1
+    r = ((np.arange(n) - add) % n) * mul_inv % n                     # R-MAT id behind every output row
+    ones = np.array([bin(int(x)).count("1") for x in r])
+    lam = 16.0 * n * (0.76 ** (12 - ones)) * (0.24 ** ones)
+    assert np.all(np.abs(deg - lam) < 1.0 + 1e-9)                     # stochastic rounding of the expectation
+    indeg = np.bincount(indices, minlength=n)
+    assert np.corrcoef(np.log1p(indeg), np.log1p(deg))[0, 1] > 0.8    # b == c: the column marginal mirrors the row marginal

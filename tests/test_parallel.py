@@ -60,6 +60,22 @@ def _cpu_worker(rank, world, port, q):
         assert bool(((mine_b >= bounds[rank]) & (mine_b < bounds[rank + 1])).all())
         dist.all_gather_object(got, mine_b.tolist())
         assert sorted(sum(got, [])) == sorted(sum(sent, []))
+        # data-parallel training plumbing: broadcast of the initial weights, ONE packed gradient all-reduce per step
+        torch.manual_seed(rank)
+        params = [torch.randn(3, 4, requires_grad=True), torch.randn(5, requires_grad=True), torch.randn(2, requires_grad=True)]
+        parallel.broadcast_parameters(params, 0)
+        ref = [None] * world
+        dist.all_gather_object(ref, [p.detach().clone() for p in params])
+        assert all(torch.equal(a, b) for a, b in zip(ref[0], ref[1]))
+        params[0].grad = torch.full((3, 4), float(rank + 1))
+        params[1].grad = torch.arange(5, dtype=torch.float32) * (rank + 1)
+        if rank == 0:
+            params[2].grad = torch.ones(2)                    # rank 1 has no gradient for this one: counts as zeros
+        nbytes = parallel.allreduce_gradients(params)
+        assert nbytes == (12 + 5 + 2) * 4
+        assert torch.equal(params[0].grad, torch.full((3, 4), 1.5))
+        assert torch.equal(params[1].grad, torch.arange(5, dtype=torch.float32) * 1.5)
+        assert torch.equal(params[2].grad, torch.full((2,), 0.5))
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
@@ -263,3 +279,55 @@ def test_partitioned_forward_single_rank_vs_oracle(kind, concat, dim):
         assert rel_err(out, ref) < 1e-4, (kind, math)
     gs.set_default_math("fp32")
     shard.close()
+
+
+def _gpu_train_worker(rank, world, port, q):
+    """config 4 in miniature: unsupervised GraphSAGE, node-partitioned features, data-parallel over 2 GPUs - the weights
+    must stay bit-identical on both ranks after every step (same initial weights, one gradient all-reduce per step), and
+    a 1-rank run on the union batch with averaged loss must give the same first update."""
+    try:
+        _init(rank, world, port, "nccl")
+        import graphsage_b200 as gs
+        from graphsage_b200 import parallel
+        rs = np.random.RandomState(0)
+        n, md, f, B = 2000, 16, 32, 48
+        adj = rs.randint(0, n, size=(n + 1, md)).astype(np.int32)
+        adj[n] = n
+        feats = rs.randn(n, f).astype(np.float32)
+        deg = rs.randint(1, 30, size=n).astype(np.float64)
+        dev = torch.device("cuda", rank)
+        bounds = parallel.uniform_bounds(n, world)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        shard = parallel.ShardedFeatures(feats[lo:hi], n, row_start=bounds)
+        adj_dev = torch.from_numpy(adj).to(dev)
+        gs.set_default_math("fp32")
+        gs.inits.manual_seed(100 + rank, dev)                     # DIFFERENT initial weights per rank: the broadcast must fix that
+        sampler = gs.UniformNeighborSampler(adj_dev, seed=123)
+        infos = [gs.SAGEInfo("node", sampler, 5, 16), gs.SAGEInfo("node", sampler, 3, 16)]
+        m = gs.UnsupervisedGraphsage({"batch_size": B, "dropout": 0.}, shard, adj_dev, deg, infos, concat=True,
+                                     aggregator_type="mean", neg_sample_size=7, learning_rate=0.01, device=dev,
+                                     distributed=True, seed=50 + rank)
+        for step in range(3):
+            b1 = torch.from_numpy(rs.randint(lo, hi, size=B).astype(np.int32))
+            b2 = torch.from_numpy(adj[b1.numpy(), step % md].astype(np.int32))
+            loss = m.train_step(b1, b2)
+            assert np.isfinite(float(loss)) and m.last_allreduce_bytes == sum(p.numel() for p in m.parameters()) * 4
+            mine = torch.cat([p.detach().reshape(-1) for p in m.parameters()]).cpu()
+            both = [None] * world
+            dist.all_gather_object(both, mine)
+            assert torch.equal(both[0], both[1]), "weights diverged after step %d" % step
+        shard.close()
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_unsupervised_data_parallel_two_gpus():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    _run(_gpu_train_worker, 2)
