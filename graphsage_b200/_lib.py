@@ -66,7 +66,7 @@ _SIGNATURES = {
     "gs_rmat_degrees": (c_i32, [c_i32, c_i64, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                 ctypes.c_double, c_u64, c_u64, c_u64, c_u64, c_vp, c_vp]),
     "gs_rmat_fill": (c_i32, [c_i32, c_i64, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_u64, c_u64,
-                             c_u64, c_u64, c_vp, c_vp, c_vp]),
+                             c_u64, c_u64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "gs_segment_max": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i64, c_vp, c_i64, c_vp]),
     "gs_sage_gemm_workspace_bytes": (c_i64, [c_i64, ctypes.POINTER(GemmPart), c_i32, c_i32]),
     "gs_sage_gemm": (c_i32, [c_i64, ctypes.POINTER(GemmPart), c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp,

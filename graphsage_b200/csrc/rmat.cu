@@ -57,52 +57,68 @@ __global__ void __launch_bounds__(256) rmat_degrees_kernel(const __grid_constant
   }
 }
 
-// one warp per row, lanes stride over the row's entries
+// entry j of row y (start = indptr[y]); r / r2 / pick_thr describe the row's pre-images
+__device__ __forceinline__ void rmat_entry(const RmatParams& p, int64_t y, int64_t r, int64_t r2, uint32_t pick_thr, int64_t j,
+                                           int64_t start, int32_t* __restrict__ indices) {
+  uint32_t hw[32];
+#pragma unroll
+  for (int blk = 0; blk < 4; ++blk) {
+    u32x4 ctr{(uint32_t)j, (uint32_t)blk, (uint32_t)y, kRmatTagFill};
+    const u32x4 rnd = philox4x32_10(ctr, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+    const uint32_t w[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      hw[blk * 8 + 2 * q] = w[q] & 0xffffu;
+      hw[blk * 8 + 2 * q + 1] = w[q] >> 16;
+    }
+  }
+  const int64_t x = (hw[0] < pick_thr) ? r2 : r;
+  int64_t col = 0;
+#pragma unroll
+  for (int l = 0; l < 31; ++l) {
+    if (l < p.scale) {
+      const int rb = (int)((x >> (p.scale - 1 - l)) & 1);
+      const int cb = hw[1 + l] < (rb ? p.thr1 : p.thr0) ? 1 : 0;
+      col = (col << 1) | cb;
+    }
+  }
+  col %= p.n;
+  int64_t cy = rmat_scramble(p, col);
+  if (cy == y) cy = (cy + 1) % p.n;
+  indices[start + j] = (int32_t)cy;
+}
+
+__device__ __forceinline__ uint32_t rmat_pick_thr(const RmatParams& p, int64_t r, int64_t r2) {
+  if (r2 >= ((int64_t)1 << p.scale)) return 0u;                      // P(pre-image = r + n), as a 16-bit threshold
+  const double p1 = p.prow[__popcll((unsigned long long)r)], p2 = p.prow[__popcll((unsigned long long)r2)];
+  return (uint32_t)(65536.0 * (p2 / (p1 + p2)));
+}
+
+// one warp per row, lanes stride over the row's entries; rows longer than `long_threshold` are left to rmat_fill_long_kernel
+// (R-MAT's hubs: at scale 27 one row has 1.2 M entries - a single warp would need half a minute for it)
 __global__ void __launch_bounds__(256) rmat_fill_kernel(const __grid_constant__ RmatParams p, const int64_t* __restrict__ indptr,
-                                                        int32_t* __restrict__ indices) {
+                                                        int32_t* __restrict__ indices, int64_t long_threshold) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t space = (int64_t)1 << p.scale;
   for (int64_t y = warp; y < p.n; y += nwarps) {
     const int64_t start = indptr[y], deg = indptr[y + 1] - start;
-    if (deg <= 0) continue;
-    const int64_t r = rmat_unscramble(p, y);
-    const int64_t r2 = r + p.n;
-    uint32_t pick_thr = 0;                                  // P(pre-image = r + n), as a 16-bit threshold
-    if (r2 < space) {
-      const double p1 = p.prow[__popcll((unsigned long long)r)], p2 = p.prow[__popcll((unsigned long long)r2)];
-      pick_thr = (uint32_t)(65536.0 * (p2 / (p1 + p2)));
-    }
-    for (int64_t j = lane; j < deg; j += 32) {
-      uint32_t hw[32];
-#pragma unroll
-      for (int blk = 0; blk < 4; ++blk) {
-        u32x4 ctr{(uint32_t)j, (uint32_t)blk, (uint32_t)y, kRmatTagFill};
-        const u32x4 rnd = philox4x32_10(ctr, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-        const uint32_t w[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          hw[blk * 8 + 2 * q] = w[q] & 0xffffu;
-          hw[blk * 8 + 2 * q + 1] = w[q] >> 16;
-        }
-      }
-      const int64_t x = (hw[0] < pick_thr) ? r2 : r;
-      int64_t col = 0;
-#pragma unroll
-      for (int l = 0; l < 31; ++l) {
-        if (l < p.scale) {
-          const int rb = (int)((x >> (p.scale - 1 - l)) & 1);
-          const int cb = hw[1 + l] < (rb ? p.thr1 : p.thr0) ? 1 : 0;
-          col = (col << 1) | cb;
-        }
-      }
-      col %= p.n;
-      int64_t cy = rmat_scramble(p, col);
-      if (cy == y) cy = (cy + 1) % p.n;
-      indices[start + j] = (int32_t)cy;
-    }
+    if (deg <= 0 || deg > long_threshold) continue;
+    const int64_t r = rmat_unscramble(p, y), r2 = r + p.n;
+    const uint32_t pick_thr = rmat_pick_thr(p, r, r2);
+    for (int64_t j = lane; j < deg; j += 32) rmat_entry(p, y, r, r2, pick_thr, j, start, indices);
   }
+}
+
+// the long rows (ids listed by the caller): blockIdx.y = which long row, the x-dimension strides over its entries
+__global__ void __launch_bounds__(256) rmat_fill_long_kernel(const __grid_constant__ RmatParams p, const int64_t* __restrict__ indptr,
+                                                             const int64_t* __restrict__ long_rows, int32_t* __restrict__ indices) {
+  const int64_t y = long_rows[blockIdx.y];
+  const int64_t start = indptr[y], deg = indptr[y + 1] - start;
+  const int64_t r = rmat_unscramble(p, y), r2 = r + p.n;
+  const uint32_t pick_thr = rmat_pick_thr(p, r, r2);
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < deg; j += (int64_t)gridDim.x * blockDim.x)
+    rmat_entry(p, y, r, r2, pick_thr, j, start, indices);
 }
 
 static int32_t fill_params(RmatParams& p, int32_t scale, int64_t n, double edge_factor, double a, double b, double c, double d,
@@ -144,16 +160,23 @@ int32_t gs_rmat_degrees(int32_t scale, int64_t n_nodes, double edge_factor, doub
 }
 
 int32_t gs_rmat_fill(int32_t scale, int64_t n_nodes, double a, double b, double c, double d, uint64_t seed, uint64_t mul,
-                     uint64_t mul_inv, uint64_t add, const int64_t* indptr, int32_t* indices, void* stream) {
+                     uint64_t mul_inv, uint64_t add, const int64_t* indptr, int32_t* indices, const int64_t* long_rows,
+                     int64_t n_long, int64_t long_threshold, void* stream) {
   gs::RmatParams p;
   const int32_t rc = gs::fill_params(p, scale, n_nodes, 1.0, a, b, c, d, seed, mul, mul_inv, add);
   if (rc != GS_OK) return rc;
   GS_REQUIRE(indptr != nullptr && indices != nullptr, "gs_rmat_fill: NULL pointer");
+  GS_REQUIRE(n_long >= 0 && n_long <= 65535 && (n_long == 0 || (long_rows != nullptr && long_threshold > 0)),
+             "gs_rmat_fill: bad long-row list (at most 65535 rows; raise the threshold)");
   int64_t blocks = (n_nodes + 7) / 8;
   int64_t cap = (int64_t)gs::sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  gs::rmat_fill_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, indptr, indices);
-  return gs::launch_check("rmat_fill_kernel");
+  gs::rmat_fill_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, indptr, indices,
+                                                                          n_long > 0 ? long_threshold : (int64_t)1 << 62);
+  int32_t rc2 = gs::launch_check("rmat_fill_kernel");
+  if (rc2 != GS_OK || n_long == 0) return rc2;
+  gs::rmat_fill_long_kernel<<<dim3(64, (unsigned)n_long), 256, 0, (cudaStream_t)stream>>>(p, indptr, long_rows, indices);
+  return gs::launch_check("rmat_fill_long_kernel");
 }
 
 }  // extern "C"

@@ -108,7 +108,8 @@ def rmat_scramble_constants(n):
     return mul, pow(mul, -1, n), 0x7F4A7C15 % n
 
 
-def rmat_csr_device(scale, n_nodes=None, edge_factor=20.0, a=0.57, b=0.19, c=0.19, d=0.05, seed=123, device="cuda"):
+def rmat_csr_device(scale, n_nodes=None, edge_factor=20.0, a=0.57, b=0.19, c=0.19, d=0.05, seed=123, device="cuda",
+                    long_threshold=4096):
     """R-MAT graph written directly as CSR on the device (gs_rmat_degrees -> prefix sum -> gs_rmat_fill; contract in
     csrc/rmat.cu / oracle/rmat.py).  Returns (indptr int64 [n+1], indices int32 [m]) CUDA tensors.  BASELINE configs[4]:
     scale=27, n_nodes=100_000_000 (8 GB of indices)."""
@@ -126,6 +127,11 @@ def rmat_csr_device(scale, n_nodes=None, edge_factor=20.0, a=0.57, b=0.19, c=0.1
         torch.cumsum(deg, dim=0, out=indptr[1:])
         m = int(indptr[-1].item())
         indices = torch.empty((m,), dtype=torch.int32, device=dev)
+        threshold = int(long_threshold)                    # rows beyond this are filled by a whole grid, not one warp
+        long_rows = torch.nonzero(deg > threshold).reshape(-1)
+        while long_rows.numel() > 65535:
+            threshold *= 2
+            long_rows = torch.nonzero(deg > threshold).reshape(-1)
         check(lib().gs_rmat_fill(scale, n, a, b, c, d, seed & (2**64 - 1), mul, mul_inv, add, ptr(indptr), ptr(indices),
-                                 stream_ptr()))
+                                 ptr(long_rows) if long_rows.numel() else 0, long_rows.numel(), threshold, stream_ptr()))
     return indptr, indices

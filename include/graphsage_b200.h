@@ -222,8 +222,11 @@ int32_t gs_cast_rows_bf16(const float* x, int64_t n, int32_t F, int64_t ldx, voi
  * --------------------------------------------------------------------------------------------- */
 int32_t gs_rmat_degrees(int32_t scale, int64_t n_nodes, double edge_factor, double a, double b, double c, double d,
                         uint64_t seed, uint64_t mul, uint64_t mul_inv, uint64_t add, int32_t* deg_out, void* stream);
+/* long_rows (device int64 [n_long], may be NULL with n_long = 0): the rows with more than long_threshold entries - R-MAT's
+ * hubs (1.2 M entries in one row at scale 27); they are filled by a whole grid each instead of one warp.  n_long <= 65535. */
 int32_t gs_rmat_fill(int32_t scale, int64_t n_nodes, double a, double b, double c, double d, uint64_t seed, uint64_t mul,
-                     uint64_t mul_inv, uint64_t add, const int64_t* indptr, int32_t* indices, void* stream);
+                     uint64_t mul_inv, uint64_t add, const int64_t* indptr, int32_t* indices, const int64_t* long_rows,
+                     int64_t n_long, int64_t long_threshold, void* stream);
 
 /* segmented max over fixed fanout: out[i, c] = max_j x[i*k + j, c]   (aggregators.py:182) */
 int32_t gs_segment_max(const float* x, int64_t n, int32_t k, int32_t C, int64_t ldx,

@@ -781,10 +781,11 @@ def test_build_padded_adj_bit_exact(gs):
 @pytest.mark.parametrize("scale,n", [(13, 5000), (10, 1024), (12, 4095)])
 def test_rmat_generator_bit_exact(gs, scale, n):
     from graphsage_b200.synthetic import rmat_csr_device
-    indptr, indices = rmat_csr_device(scale, n, 20.0, seed=11)
     ref_ptr, ref_idx = oracle.rmat.rmat_csr(scale, n, 20.0, seed=11)
-    np.testing.assert_array_equal(indptr.cpu().numpy(), ref_ptr)
-    np.testing.assert_array_equal(indices.cpu().numpy(), ref_idx)
+    for threshold in (4096, 50):                       # 50: the hub rows take the whole-grid path
+        indptr, indices = rmat_csr_device(scale, n, 20.0, seed=11, long_threshold=threshold)
+        np.testing.assert_array_equal(indptr.cpu().numpy(), ref_ptr)
+        np.testing.assert_array_equal(indices.cpu().numpy(), ref_idx)
 
 
 def test_rmat_generator_properties_at_scale(gs):
