@@ -447,6 +447,10 @@ __global__ void __launch_bounds__(256) maxpool_pack128_kernel(const float* __res
 
 __device__ __forceinline__ void tma_gather4(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int col, int r0, int r1,
                                             int r2, int r3);
+__device__ __forceinline__ void tma_gather4_multicast(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, uint16_t mask,
+                                                      int col, int r0, int r1, int r2, int r3);
+__device__ __forceinline__ uint32_t cluster_ctarank();
+__device__ __forceinline__ void cluster_sync_all();
 
 // table row of tile row r of a CTA's local tile tl (padding rows of a tile read row 0: finite data the epilogue never
 // looks at)
@@ -1136,6 +1140,260 @@ __global__ void __launch_bounds__(MPT_THREADS, 1) maxpool_mlp_tmem_kernel(const 
   }
 }
 
+// Cluster form (k4_cluster = 1, the default when hidden / 128 is 2, 4 or 8): the CTAs that hold the hidden slices of ONE
+// tile form a thread-block cluster of CL = hidden / 128 CTAs.  Each CTA gathers only 128 / CL of the tile's rows - with the
+// TMA row gather, `cp.async.bulk.tensor.2d.tile::gather4` (four table rows named by index, 128 bytes each, SWIZZLE_128B
+// applied by the tensor map, columns >= K zero-filled) - and MULTICASTS them into the same stage of every CTA of the
+// cluster, so a gathered row crosses the L2 -> SM fabric once per tile instead of once per slice: 163 MB per launch
+// instead of 650 MB (the fabric, saturated by 128-byte random pieces at 5.4 TB/s, was what held every one-CTA-per-slice
+// variant at 121 us).  Hand-off: a CTA's full barrier = its own expect_tx arrive + 16 KB of transactions from all CL
+// issuers; its empty barrier counts CL arrivals - every CTA's MMA warp commits with .multicast::cluster to all CL empty
+// barriers -, so a stage is refilled only when the whole cluster has consumed it.  Producer warp w owns the ring slots
+// w, w + MPC_PW, ... (n_stages is a multiple of MPC_PW: a slot is always filled by the same warp, so a wait is never more
+// than one phase ahead - tools/pipeline_model.py).  No cp.async groups, no proxy fence, no per-thread address arithmetic.
+constexpr int MPC_PW = 4;                         // producer warps
+constexpr int MPC_THREADS = (MPC_PW + 6) * 32;
+
+template <int CL>
+__global__ void __launch_bounds__(MPC_THREADS, 1)
+    maxpool_mlp_tmemc_kernel(const __grid_constant__ MpParams prm, const __grid_constant__ CUtensorMap tmap) {
+  constexpr int KC = 64, NT = 128;
+  constexpr int NBUF = 2;
+  constexpr int X_IMG = NT * 128;
+  constexpr int ROWS_PER_CTA = NT / CL;             // this CTA's share of the tile's rows
+  constexpr int LANES = ROWS_PER_CTA / 4;           // one gather4 (4 rows) per active lane
+  constexpr uint16_t MASK = (uint16_t)((1u << CL) - 1u);
+  static_assert(CL == 2 || CL == 4 || CL == 8, "cluster = the 2, 4 or 8 hidden slices of one tile");
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_x[MPT_MAX_STAGES], empty_x[MPT_MAX_STAGES], acc_full[2], acc_empty[2], w_full, wt_full;
+  __shared__ uint32_t tmem_base_smem;
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int kblocks = prm.kblocks, kb_t = prm.kb_t, kb_s = kblocks - kb_t;
+  const int n_stages = prm.n_stages;
+  unsigned char* w_res = smem;                                        // K-blocks kb_t.. of the weight slice (SS operands)
+  unsigned char* x_ring = smem + (size_t)kb_s * MPT_IMG;     // n_stages stages of X_IMG bytes
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x % prm.n_slices;
+  const int64_t tile0 = blockIdx.x / prm.n_slices, tile_step = gridDim.x / prm.n_slices;
+  const int k = prm.k, G = prm.G;
+  const int rows_valid = G * k;
+  const int64_t total_rows = prm.n_groups * (int64_t)k;
+  const int64_t my_tiles = tile0 < prm.n_tiles ? (prm.n_tiles - tile0 + tile_step - 1) / tile_step : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MPT_MAX_STAGES; ++s) {
+      mbar_init(&full_x[s], 1);                     // own expect_tx arrive; the 16 KB arrive from all CL issuers
+      mbar_init(&empty_x[s], CL);                   // one multicast commit per CTA of the cluster
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);                  // one arrive per epilogue warp
+    }
+    mbar_init(&w_full, 1);
+    mbar_init(&wt_full, 4);                         // one arrive per epilogue warp (each writes its 32 TMEM lanes)
+    fence_mbar_init();
+  }
+  if (warp == MPC_PW + 1) {
+    tmem_alloc(&tmem_base_smem, 512);               // 2 x 128 accumulator columns + up to 256 weight columns
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                               // every CTA's barriers exist before any remote arrive / multicast write
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp < MPC_PW) {
+    // =============================== gather producers (TMA gather4, multicast) ===============================
+    const int rank = (int)cluster_ctarank();        // == slice: the cluster spans the hidden slices of one tile
+    const int row_base = rank * ROWS_PER_CTA + 4 * lane;
+    const int64_t total_it = my_tiles * kblocks;
+    int raw[4], cur[4];
+    auto request = [&](int64_t tl) {                // ids of tile tl: loads only (nothing depends on them yet)
+      const int64_t t = tile0 + tl * tile_step;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = row_base + i;
+        const int64_t flat = t * rows_valid + r;
+        const bool live = lane < LANES && tl < my_tiles && r < rows_valid && flat < total_rows;
+        int v = 0;                                  // padding rows of a tile read row 0 (finite data, never looked at)
+        if (live) v = prm.row_ids ? __ldg(prm.row_ids + flat) : (int)(prm.row0 + flat);
+        raw[i] = v;
+      }
+    };
+    auto finish = [&]() {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int id = raw[i];
+        if (id < 0 || (int64_t)id >= prm.n_rows) id = (int)(prm.n_rows - 1);
+        cur[i] = id;
+      }
+    };
+    int64_t tl = 0;
+    int kb = warp;
+    while (kb >= kblocks) { kb -= kblocks; ++tl; }
+    request(tl);
+    finish();
+    request(tl + 1);
+    for (int64_t it = warp; it < total_it; it += MPC_PW) {
+      const uint32_t s = (uint32_t)(it % n_stages);
+      const uint32_t fill = (uint32_t)(it / n_stages);
+      mbar_wait(&empty_x[s], (fill & 1u) ^ 1u);     // every CTA of the cluster has consumed the previous fill
+      if (lane == 0) mbar_expect_tx(&full_x[s], (uint32_t)X_IMG);
+      __syncwarp();
+      if (lane < LANES)
+        tma_gather4_multicast(x_ring + (size_t)s * X_IMG + (size_t)row_base * 128, &tmap, &full_x[s], MASK, kb * KC, cur[0],
+                              cur[1], cur[2], cur[3]);
+      kb += MPC_PW;
+      if (kb >= kblocks) {
+        int adv = 0;
+        while (kb >= kblocks) { kb -= kblocks; ++adv; }
+        tl += adv;
+        if (adv != 1) request(tl);
+        finish();
+        request(tl + 1);
+      }
+    }
+  } else if (warp == MPC_PW) {
+    // =============================== MMA issuer ===============================
+    constexpr uint32_t idesc = make_idesc(1u, 128, NT);               // bf16 x bf16 -> fp32, M = 128, N = 128
+    if (kb_s > 0) mbar_wait_uniform(&w_full, 0);
+    if (kb_t > 0) mbar_wait_uniform(&wt_full, 0);
+    tc_fence_after();
+    const uint32_t x_base = smem_u32(x_ring), w_base = smem_u32(w_res);
+    uint32_t s = 0, ph = 0;
+    for (int64_t tl = 0; tl < my_tiles; ++tl) {
+      const uint32_t buf = NBUF == 2 ? ((uint32_t)tl & 1u) : 0u;
+      const uint32_t use = (uint32_t)(NBUF == 2 ? (tl >> 1) : tl);          // how often this accumulator has been used before
+      mbar_wait_uniform(&acc_empty[buf], (use & 1u) ^ 1u);                  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * (uint32_t)NT;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait_uniform(&full_x[s], ph);          // (TMA wrote the stage through the async proxy: no proxy fence)
+        tc_fence_after();
+        const uint64_t bdesc = make_smem_desc(x_base + s * (uint32_t)X_IMG);
+        if (kb < kb_t) {
+          const uint32_t a_t = tmem_base + (uint32_t)MPT_ACOL0 + (uint32_t)kb * 32u;
+#pragma unroll
+          for (int k2 = 0; k2 < KC / 16; ++k2)      // K = 16 per instruction: 8 TMEM columns of A, 32 B of B inside the atom
+            umma_ts_elect_bf16(tmem_acc, a_t + (uint32_t)(k2 * 8), bdesc + (uint64_t)(k2 * 2), idesc, (kb > 0 || k2 > 0) ? 1u : 0u);
+        } else {
+          const uint64_t adesc = make_smem_desc(w_base + (uint32_t)(kb - kb_t) * (uint32_t)MPT_IMG);
+#pragma unroll
+          for (int k2 = 0; k2 < KC / 16; ++k2)
+            umma_ss_elect<true>(tmem_acc, adesc + (uint64_t)(k2 * 2), bdesc + (uint64_t)(k2 * 2), idesc, (kb > 0 || k2 > 0) ? 1u : 0u);
+        }
+        umma_commit_elect_multicast(&empty_x[s], MASK);     // frees the stage in every CTA of the cluster
+        if (kb == kblocks - 1) umma_commit_elect(&acc_full[buf]);
+        if (++s == (uint32_t)n_stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == MPC_PW + 1) {
+    // =============================== shared-memory part of the weight slice ===============================
+    if (lane == 0 && kb_s > 0) {
+      mbar_expect_tx(&w_full, (uint32_t)(kb_s * MPT_IMG));
+      const unsigned char* src = prm.wimg + ((int64_t)slice * kblocks + kb_t) * MPT_IMG;
+      for (int kb = 0; kb < kb_s; ++kb) bulk_g2s(w_res + (size_t)kb * MPT_IMG, src + (int64_t)kb * MPT_IMG, MPT_IMG, &w_full);
+    }
+    __syncwarp();
+  } else {
+    // =============================== epilogue warps ===============================
+    const int q = warp & 3;                         // TMEM lane quarter of this warp (four consecutive warps cover 0..3)
+    const int h = slice * 128 + q * 32 + lane;      // this thread's hidden unit = its TMEM lane
+    // once: this lane's row of Wm^T (bf16 pairs) for the first kb_t K-blocks -> tensor memory (A operand, TS form)
+    {
+      const uint32_t* wrow = prm.wrows + (int64_t)h * (kblocks * 32);
+      const uint32_t t_a = tmem_base + (uint32_t)MPT_ACOL0 + ((uint32_t)(q * 32) << 16);
+      for (int cb = 0; cb < kb_t; ++cb) {
+        uint32_t r[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(wrow + cb * 32) + j);
+          r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
+        }
+        tmem_st_32x32(t_a + (uint32_t)(cb * 32), r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&wt_full);
+    }
+    const float b = prm.bias ? prm.bias[h] : 0.f;
+    const float inv_k = 1.0f / (float)k;
+    const bool mean = prm.pool_mean != 0;
+    auto fold = [&](float m, uint32_t x) -> float {
+      const float v = __uint_as_float(x);
+      // mean-pool (reference aggregators.py:246-273): ReLU does not commute with the mean, so bias + ReLU are applied
+      // per element and summed in j order; max-pool: bias + ReLU after the max (they commute with it)
+      return mean ? m + fmaxf(v + b, 0.f) : fmaxf(m, v);
+    };
+    for (int64_t tl = 0; tl < my_tiles; ++tl) {
+      const int64_t t = tile0 + tl * tile_step;
+      const uint32_t buf = NBUF == 2 ? ((uint32_t)tl & 1u) : 0u;
+      const uint32_t use = (uint32_t)(NBUF == 2 ? (tl >> 1) : tl);
+      const int64_t g_base = t * G;
+      const int groups_here = (int)min((int64_t)G, prm.n_groups - g_base);
+      mbar_wait(&acc_full[buf], use & 1u);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * (uint32_t)NT + ((uint32_t)(q * 32) << 16);
+      float* outp = prm.out + g_base * prm.ldo + h;
+      // one fanout group = k consecutive accumulator columns of this lane, fetched in pieces of 32 / 16 / 8 / 4 / 2 / 1
+      // columns chosen by the bits of k: statically indexed registers, straight-line pooling (see the wide kernel)
+      for (int g = 0; g < groups_here; ++g) {
+        uint32_t col = tmem_acc + (uint32_t)(g * k);
+        float m = mean ? 0.f : -3.0e38f;
+        int rem = k;
+        while (rem >= 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(col, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m = fold(m, r[j]);
+          col += 32u;
+          rem -= 32;
+        }
+        uint32_t r16[16], r8[8], r4[4], r2[2], r1[1];
+        uint32_t cc = col;
+        if (rem & 16) { tmem_ld_32x16(cc, r16); cc += 16u; }
+        if (rem & 8) { tmem_ld_32x8(cc, r8); cc += 8u; }
+        if (rem & 4) { tmem_ld_32x4(cc, r4); cc += 4u; }
+        if (rem & 2) { tmem_ld_32x2(cc, r2); cc += 2u; }
+        if (rem & 1) { tmem_ld_32x1(cc, r1); }
+        tmem_ld_wait();
+        if (rem & 16) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) m = fold(m, r16[j]);
+        }
+        if (rem & 8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) m = fold(m, r8[j]);
+        }
+        if (rem & 4) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) m = fold(m, r4[j]);
+        }
+        if (rem & 2) {
+          m = fold(m, r2[0]);
+          m = fold(m, r2[1]);
+        }
+        if (rem & 1) m = fold(m, r1[0]);
+        outp[(int64_t)g * prm.ldo] = mean ? m * inv_k : fmaxf(m + b, 0.f);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();                               // no CTA leaves while a peer may still write its stages or signal its barriers
+  if (warp == MPC_PW + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+
 // Two pipelines per CTA (k4_kernel = 0 with k4_tile = 128 and k4_pipes = 2, the default): the NT = 128 kernel showed the
 // single MMA warp saturated - ~860 cycles of instruction latency per four-MMA K-block, tensor pipe idle 70 % - and never
 // short of operands.  Here the CTA runs TWO independent producer -> MMA chains that share only the weights in TMEM, the
@@ -1723,6 +1981,45 @@ static int32_t pool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K,
     int64_t ctas_t = (int64_t)(gs::sm_count() / prm.n_slices) * prm.n_slices;   // a whole number of slice groups
     if (ctas_t < prm.n_slices) ctas_t = prm.n_slices;
     if (ctas_t > prm.n_tiles * prm.n_slices) ctas_t = prm.n_tiles * prm.n_slices;
+    if (nt == 128 && gs::tuning("k4_cluster", 1) == 1 && (prm.n_slices == 2 || prm.n_slices == 4 || prm.n_slices == 8) &&
+        prm.n_stages >= gs::MPC_PW) {
+      prm.n_stages -= prm.n_stages % gs::MPC_PW;         // a ring slot is always filled by the same producer warp
+      CUtensorMap tmap;
+      const int32_t rcm = make_table_tensor_map(&tmap, table_bf16, n_rows, K, pitch, 64);
+      if (rcm != GS_OK) return rcm;
+      const void* fnc = prm.n_slices == 2   ? (const void*)gs::maxpool_mlp_tmemc_kernel<2>
+                        : prm.n_slices == 4 ? (const void*)gs::maxpool_mlp_tmemc_kernel<4>
+                                            : (const void*)gs::maxpool_mlp_tmemc_kernel<8>;
+      const int32_t rcc = gs::ensure_dyn_smem(fnc, gs::MPW_SMEM);
+      if (rcc != GS_OK) return rcc;
+      if (prm.n_slices == 8) GS_CUDA(cudaFuncSetAttribute(fnc, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)ctas_t);              // a multiple of n_slices: whole clusters
+      cfg.blockDim = dim3((unsigned)gs::MPC_THREADS);
+      cfg.dynamicSmemBytes = gs::MPW_SMEM;
+      cfg.stream = (cudaStream_t)stream;
+      cudaLaunchAttribute attr;
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = (unsigned)prm.n_slices;
+      attr.val.clusterDim.y = 1;
+      attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      // persistent clusters: launch only as many as can be resident at once (a GPC whose SM count is not a multiple of the
+      // cluster size leaves SMs over, so 148 SMs do not always hold 148 / CL clusters)
+      static int max_clusters[3] = {0, 0, 0};
+      int& mc = max_clusters[prm.n_slices == 2 ? 0 : prm.n_slices == 4 ? 1 : 2];
+      if (mc == 0) {
+        int n = 0;
+        GS_CUDA(cudaOccupancyMaxActiveClusters(&n, fnc, &cfg));
+        mc = n > 0 ? n : 1;
+      }
+      if ((int64_t)mc * prm.n_slices < ctas_t) cfg.gridDim = dim3((unsigned)(mc * prm.n_slices));
+      void* args[2] = {(void*)&prm, (void*)&tmap};
+      GS_CUDA(cudaLaunchKernelExC(&cfg, fnc, args));
+      return gs::launch_check("maxpool_mlp_tmemc_kernel");
+    }
     if (nt == 128 && gs::tuning("k4_pipes", 1) == 2 && prm.n_stages >= 4) {
       prm.n_stages &= ~1;                               // two half rings
       const int32_t rc2 = gs::ensure_dyn_smem((const void*)gs::maxpool_mlp_tmem2_kernel, gs::MPW_SMEM);

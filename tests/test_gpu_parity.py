@@ -591,7 +591,7 @@ def test_packed_weights_follow_weight_updates(gs):
     (3, 128, 64, 256, True),           # one group per tile
     (1000, 1, 602, 1024, True),        # k = 1 (max over a single row), "big" hidden
 ])
-@pytest.mark.parametrize("variant", ["tmem128x2", "tmem128", "tmem256", "wide128_tma", "wide128_cpasync", "wide256_cpasync", "round1"])
+@pytest.mark.parametrize("variant", ["tmem128c", "tmem128", "tmem128x2", "tmem256", "wide128_tma", "wide128_cpasync", "wide256_cpasync", "round1"])
 def test_maxpool_mlp_fused_vs_reference(gs, case, variant):
     n_groups, k, K, hidden, use_ids = case
     if k > K4_VARIANTS[variant][2]:
@@ -600,25 +600,28 @@ def test_maxpool_mlp_fused_vs_reference(gs, case, variant):
     try:
         _maxpool_mlp_case(gs, n_groups, k, K, hidden, use_ids)
     finally:
-        _k4_select(gs, "tmem128")
+        _k4_select(gs, "tmem128c")
 
 
-# name -> (k4_kernel, k4_wide_producer, tile rows, k4_pipes)
-K4_VARIANTS = {"tmem128": (0, 1, 128, 1),          # default: weights = A operand in tensor memory, two accumulators
-               "tmem128x2": (0, 1, 128, 2),        # two producer->MMA chains per CTA
-               "tmem256": (0, 1, 256, 1),          # one chain, one 256-column accumulator
-               "wide128_tma": (3, 1, 128, 1),      # weights resident in shared memory, 128-row tiles, TMA gather4 producers
-               "wide128_cpasync": (3, 0, 128, 1),  # same geometry, cp.async producers
-               "wide256_cpasync": (2, 0, 256, 1),  # 256-row tiles, 64-byte row pieces
-               "round1": (1, 0, 128, 1)}           # gathered rows = A operand, shared-memory transpose in the epilogue
+# name -> (k4_kernel, k4_wide_producer, tile rows, k4_pipes, k4_cluster)
+K4_VARIANTS = {"tmem128c": (0, 1, 128, 1, 1),         # default: weights in tensor memory, the slices of a tile form a cluster,
+                                                      # rows gathered once per cluster by TMA gather4 multicast
+               "tmem128": (0, 1, 128, 1, 0),          # one CTA per slice gathers its own rows (cp.async)
+               "tmem128x2": (0, 1, 128, 2, 0),        # two producer->MMA chains per CTA
+               "tmem256": (0, 1, 256, 1, 0),          # one chain, one 256-column accumulator
+               "wide128_tma": (3, 1, 128, 1, 0),      # weights resident in shared memory, 128-row tiles, TMA gather4 producers
+               "wide128_cpasync": (3, 0, 128, 1, 0),  # same geometry, cp.async producers
+               "wide256_cpasync": (2, 0, 256, 1, 0),  # 256-row tiles, 64-byte row pieces
+               "round1": (1, 0, 128, 1, 0)}           # gathered rows = A operand, shared-memory transpose in the epilogue
 
 
 def _k4_select(gs, name):
-    kernel, producer, tile, pipes = K4_VARIANTS[name]
+    kernel, producer, tile, pipes, cluster = K4_VARIANTS[name]
     gs._lib.set_tuning("k4_kernel", kernel)
     gs._lib.set_tuning("k4_wide_producer", producer)
     gs._lib.set_tuning("k4_tile", tile)
     gs._lib.set_tuning("k4_pipes", pipes)
+    gs._lib.set_tuning("k4_cluster", cluster)
 
 
 def test_maxpool_mlp_fused_wide_fanouts(gs):
@@ -628,7 +631,7 @@ def test_maxpool_mlp_fused_wide_fanouts(gs):
              (900, 5, 64, 128), (333, 7, 33, 128), (260, 25, 512, 256), (260, 25, 513, 128), (1500, 25, 602, 128))
     wide = ((7, 200, 602, 128), (2, 256, 64, 256), (11, 129, 300, 128), (700, 9, 32, 128))
     try:
-        for name in ("tmem128x2", "tmem128", "tmem256", "wide128_tma", "wide128_cpasync", "wide256_cpasync"):
+        for name in ("tmem128c", "tmem128", "tmem128x2", "tmem256", "wide128_tma", "wide128_cpasync", "wide256_cpasync"):
             _k4_select(gs, name)
             tile = K4_VARIANTS[name][2]
             for case in cases + (wide if tile == 256 else ()):
@@ -636,7 +639,7 @@ def test_maxpool_mlp_fused_wide_fanouts(gs):
             with pytest.raises(RuntimeError, match="k <= %d" % tile):
                 _maxpool_mlp_case(gs, 2, tile + 1, 64, 128, True)
     finally:
-        _k4_select(gs, "tmem128")
+        _k4_select(gs, "tmem128c")
 
 
 def _maxpool_mlp_case(gs, n_groups, k, K, hidden, use_ids):

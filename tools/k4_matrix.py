@@ -29,17 +29,19 @@ def timeit(n=16):
 
 
 flops = 2.0 * B * 250 * F * H
-for name, ksel, prod, tile, pipes in (("tmem 128 x 2 pipelines", 0, 1, 128, 2), ("tmem 128-row tiles", 0, 1, 128, 1),
-                                      ("tmem 256-row tiles", 0, 1, 256, 1), ("wide128 + TMA gather4", 3, 1, 128, 1),
-                                      ("wide128 + cp.async", 3, 0, 128, 1), ("wide256 + cp.async", 2, 0, 256, 1),
-                                      ("round 1", 1, 0, 128, 1)):
+for name, ksel, prod, tile, pipes, cluster in (("tmem 128 + cluster multicast", 0, 1, 128, 1, 1), ("tmem 128-row tiles", 0, 1, 128, 1, 0),
+                                               ("tmem 128 x 2 pipelines", 0, 1, 128, 2, 0), ("tmem 256-row tiles", 0, 1, 256, 1, 0),
+                                               ("wide128 + TMA gather4", 3, 1, 128, 1, 0), ("wide128 + cp.async", 3, 0, 128, 1, 0),
+                                               ("wide256 + cp.async", 2, 0, 256, 1, 0), ("round 1", 1, 0, 128, 1, 0)):
     lib.gs_set_tuning(b"k4_kernel", ksel)
     lib.gs_set_tuning(b"k4_wide_producer", prod)
     lib.gs_set_tuning(b"k4_tile", tile)
     lib.gs_set_tuning(b"k4_pipes", pipes)
+    lib.gs_set_tuning(b"k4_cluster", cluster)
     t = timeit()
-    print("%-24s: %.1f us  %.1f TFLOP/s" % (name, t, flops / t / 1e6), flush=True)
+    print("%-28s: %.1f us  %.1f TFLOP/s" % (name, t, flops / t / 1e6), flush=True)
 lib.gs_set_tuning(b"k4_kernel", 0)
 lib.gs_set_tuning(b"k4_wide_producer", 1)
 lib.gs_set_tuning(b"k4_tile", 128)
 lib.gs_set_tuning(b"k4_pipes", 1)
+lib.gs_set_tuning(b"k4_cluster", 1)
