@@ -464,7 +464,15 @@ def main():
                    "replica_rows_per_gpu": int(len(hot)), "replica_fraction_of_table": float(len(hot)) / N_NODES,
                    "gather_kernel_ms": pr["gather_kernel_ms"],
                    "nvlink_GBps_per_gpu": rho * GATHER_BYTES / (pr["gather_kernel_ms"] * 1e-3) / 1e9,
-                   "nvlink_peak_GBps": 770.0}
+                   "nvlink_peak_GBps": 770.0, "halo_staging": bool(shard.stage_halo)}
+            if shard.stage_halo:
+                # with staging the gather kernel reads local memory only; the NVLink transfer is the fetch pass, which
+                # overlaps the neighbouring steps - its rate is bounded below by (unique remote bytes / step time)
+                uniq = float(torch.unique(allids[(parallel.owner_of(allids, N_NODES, world, bounds) != rank) & (allids < N_NODES)
+                                                  & ((shard.remap[allids.clamp(0, N_NODES).long()] < 0) if shard.remap is not None else True)]).numel())
+                out["unique_remote_rows_per_step"] = uniq
+                out["nvlink_GBps_per_gpu"] = uniq * F * 4 / (out["ms_per_step"] * 1e-3) / 1e9
+                out["nvlink_note"] = "unique remote rows of one step x row bytes / pipelined step time (lower bound on the fetch pass's rate)"
             if full:
                 out.update({"e2e": pr["e2e"], "e2e_ms_per_step": pr["ms_e2e"] / args.steps, "value_spread_ms": pr["ms_value"],
                             "clocks": pr["clocks"], "launches": pr["launches"],
@@ -472,8 +480,8 @@ def main():
                                 min(np.diff(bounds)), max(np.diff(bounds))),
                             "note": "node-partitioned features (contiguous community-aligned ranges), adjacency replicated, "
                                     "remote rows pulled by the gather kernel over NVLink peer mappings (one bulk copy per row), "
-                                    "the hottest remote rows replicated locally (budget: 1/8 of the table per GPU unless "
-                                    "GS_HALO_CACHE_ROWS says otherwise); owner-computes seeds"})
+                                    "the hottest remote rows replicated locally (budget: 1/4 of the table per GPU unless "
+                                    "GS_HALO_CACHE_ROWS says otherwise), (GS_HALO_STAGING=1 adds the opt-in halo staging passes); owner-computes seeds"})
             barrier()
             shard.close()
             return out

@@ -53,7 +53,11 @@ _SIGNATURES = {
     "gs_gather_mean": (c_i32, [c_vp, c_i32, c_i64, c_i32, c_i64, ctypes.POINTER(Segment), c_i32, c_i32, c_vp, c_vp,
                                c_i64, c_vp]),
     "gs_gather_mean_sharded": (c_i32, [ctypes.POINTER(ShardedTable), c_i32, c_i32, c_i64, ctypes.POINTER(Segment), c_i32,
-                                       c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
+                                       c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "gs_halo_begin": (c_i32, [c_vp, c_i64, c_vp, c_vp]),
+    "gs_halo_claim": (c_i32, [ctypes.POINTER(ShardedTable), c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "gs_halo_fetch": (c_i32, [ctypes.POINTER(ShardedTable), c_i32, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "gs_halo_translate": (c_i32, [ctypes.POINTER(ShardedTable), c_vp, c_i64, c_vp, c_vp, c_vp]),
     "gs_translate_ids": (c_i32, [ctypes.POINTER(ShardedTable), c_vp, c_i64, c_vp, c_vp]),
     "gs_gather_rows_sharded": (c_i32, [ctypes.POINTER(ShardedTable), c_i32, c_i32, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "gs_shard_alloc": (c_i32, [c_i64, ctypes.POINTER(c_vp)]),

@@ -216,11 +216,14 @@ struct ShardTab {
 struct ShardRows {
   ShardTab t;
   int64_t pitch;
-  int32_t locators;           // the id lists were translated by gs_translate_ids: >= 0 local row index, < 0 -> -(global id) - 1
+  int32_t locators;           // 0: global ids; 1: gs_translate_ids locators (>= 0 local row index, < 0 -> -(global id) - 1);
+                              // 2: gs_halo_translate locators (>= 0 local row index, < 0 -> row -(loc) - 1 of `staging`)
+  const float* staging;       // this step's halo rows, fetched once each by gs_halo_fetch (locators == 2)
   __device__ __forceinline__ const float* row(int64_t id) const {
     const float* mine = t.base[t.my_shard];
     if (locators) {
       if (id >= 0) return mine + id * pitch;
+      if (locators == 2) return staging + (-id - 1) * pitch;
       id = -id - 1;                                  // a remote row: owner found below
     } else if (id < 0 || id >= t.n_global_rows - 1) {
       return mine + t.zero_row * pitch;
@@ -492,6 +495,76 @@ __global__ void __launch_bounds__(256) translate_ids_kernel(const int32_t* __res
       if (loc < 0) loc = -id - 1;
     }
     out[i] = loc;
+  }
+}
+
+// ---- halo staging: every remote row a step needs is fetched ONCE into a local staging buffer --------------------------
+// A step's frontier names the same remote node many times (one permutation per sampler call + hub nodes: ~25 % of the
+// remote rows of a Reddit-shaped batch are repeats), and peer reads bypass the local L2, so the fused gather pulled each
+// repeat over NVLink again.  Three small passes remove that:
+//   claim     : thread per id; the first thread to see a remote id (atomicCAS on claim[id]) takes the next staging slot
+//   fetch     : warp per claimed row, 128-bit loads from the owner (peer mapping) -> staging (local HBM)
+//   translate : thread per id -> locator (>= 0: row of this GPU's own buffer; < 0: staging row -(loc) - 1)
+// after which the gather kernel reads local memory only.  The passes of step i overlap the gathers of steps i +- 1 on the
+// other streams: the NVLink transfer is no longer inside the HBM-bound kernel.
+__device__ __forceinline__ bool halo_is_local(const ShardTab& t, int32_t id, int32_t& loc) {
+  if (id < 0 || id >= t.n_global_rows - 1) { loc = (int32_t)t.zero_row; return true; }
+  if (t.remap) {
+    loc = __ldg(t.remap + id);
+    return loc >= 0;
+  }
+  if (id >= t.row_start[t.my_shard] && id < t.row_start[t.my_shard + 1]) { loc = (int32_t)(id - t.row_start[t.my_shard]); return true; }
+  return false;
+}
+
+__global__ void __launch_bounds__(256) halo_claim_kernel(const __grid_constant__ ShardTab t, const int32_t* __restrict__ ids,
+                                                         int64_t n, int32_t* __restrict__ claim, int32_t* __restrict__ count,
+                                                         int32_t* __restrict__ stage_ids, int64_t capacity) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t id = ids[i];
+    int32_t loc;
+    if (halo_is_local(t, id, loc)) continue;
+    if (atomicCAS(claim + id, -1, -2) == -1) {             // first sighting of this remote id in the step
+      const int32_t idx = atomicAdd(count, 1);
+      if (idx < capacity) stage_ids[idx] = id;
+      claim[id] = idx;                                     // read by the translate pass (a later launch)
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) halo_translate_kernel(const __grid_constant__ ShardTab t, const int32_t* __restrict__ ids,
+                                                             int64_t n, const int32_t* __restrict__ claim,
+                                                             int32_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t id = ids[i];
+    int32_t loc;
+    if (!halo_is_local(t, id, loc)) loc = -claim[id] - 1;
+    out[i] = loc;
+  }
+}
+
+// warp per staged row; every lane keeps kHaloLoads 128-bit peer loads in flight before it stores
+constexpr int kHaloLoads = 5;
+__global__ void __launch_bounds__(256) halo_fetch_kernel(const __grid_constant__ ShardRows sr, int row_f4,
+                                                         const int32_t* __restrict__ stage_ids, const int32_t* __restrict__ count,
+                                                         int64_t capacity, float* __restrict__ staging, int64_t staging_pitch) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  int64_t n = *count;
+  if (n > capacity) n = capacity;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const float4* src = reinterpret_cast<const float4*>(sr.row(stage_ids[i]));
+    float4* dst = reinterpret_cast<float4*>(staging + i * staging_pitch);
+    for (int c0 = lane; c0 < row_f4; c0 += 32 * kHaloLoads) {
+      float4 v[kHaloLoads];
+#pragma unroll
+      for (int u = 0; u < kHaloLoads; ++u)
+        if (c0 + 32 * u < row_f4) v[u] = ldg_nc_f4(src + c0 + 32 * u);
+#pragma unroll
+      for (int u = 0; u < kHaloLoads; ++u)
+        if (c0 + 32 * u < row_f4) dst[c0 + 32 * u] = v[u];
+    }
   }
 }
 
@@ -797,16 +870,75 @@ int32_t gs_translate_ids(const gs_sharded_table* table_host, const int32_t* ids,
   return gs::launch_check("translate_ids_kernel");
 }
 
+int32_t gs_halo_begin(int32_t* claim, int64_t n_global_rows, int32_t* count, void* stream) {
+  GS_REQUIRE(claim && count && n_global_rows > 0, "gs_halo_begin: bad arguments");
+  GS_CUDA(cudaMemsetAsync(claim, 0xff, (size_t)n_global_rows * 4, (cudaStream_t)stream));     // every entry = -1
+  GS_CUDA(cudaMemsetAsync(count, 0, 4, (cudaStream_t)stream));
+  return GS_OK;
+}
+
+int32_t gs_halo_claim(const gs_sharded_table* table_host, const int32_t* ids, int64_t n, int32_t* claim, int32_t* count,
+                      int32_t* stage_ids, int64_t capacity, void* stream) {
+  gs::ShardRows sr;
+  int32_t rc = fill_shard_tab(table_host, sr, 4, "gs_halo_claim");
+  if (rc != GS_OK) return rc;
+  GS_REQUIRE(n >= 0 && capacity >= 0, "gs_halo_claim: negative size");
+  if (n == 0) return GS_OK;
+  GS_REQUIRE(ids && claim && count && stage_ids, "gs_halo_claim: NULL pointer");
+  int64_t blocks = (n + 255) / 256;
+  int64_t cap = (int64_t)gs::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  gs::halo_claim_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(sr.t, ids, n, claim, count, stage_ids, capacity);
+  return gs::launch_check("halo_claim_kernel");
+}
+
+int32_t gs_halo_translate(const gs_sharded_table* table_host, const int32_t* ids, int64_t n, const int32_t* claim, int32_t* out,
+                          void* stream) {
+  gs::ShardRows sr;
+  int32_t rc = fill_shard_tab(table_host, sr, 4, "gs_halo_translate");
+  if (rc != GS_OK) return rc;
+  GS_REQUIRE(n >= 0, "gs_halo_translate: n < 0");
+  if (n == 0) return GS_OK;
+  GS_REQUIRE(ids && claim && out, "gs_halo_translate: NULL pointer");
+  int64_t blocks = (n + 255) / 256;
+  int64_t cap = (int64_t)gs::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  gs::halo_translate_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(sr.t, ids, n, claim, out);
+  return gs::launch_check("halo_translate_kernel");
+}
+
+int32_t gs_halo_fetch(const gs_sharded_table* table_host, int32_t F, int64_t pitch, const int32_t* stage_ids,
+                      const int32_t* count, int64_t capacity, float* staging, int64_t staging_pitch, void* stream) {
+  gs::ShardRows sr;
+  int32_t rc = fill_shard_tab(table_host, sr, pitch, "gs_halo_fetch");
+  if (rc != GS_OK) return rc;
+  if (capacity == 0) return GS_OK;
+  GS_REQUIRE(stage_ids && count && staging && gs::aligned16(staging) && staging_pitch % 4 == 0 && F > 0 &&
+                 pitch >= ((F + 3) / 4) * 4 && staging_pitch >= ((F + 3) / 4) * 4,
+             "gs_halo_fetch: bad arguments");
+  sr.locators = 0;
+  sr.staging = nullptr;
+  sr.t.remap = nullptr;                        // staged ids are remote by construction: resolve them by owner only
+  const int blocks = gs::sm_count() * gs::tuning("halo_fetch_ctas_per_sm", 2);
+  gs::halo_fetch_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(sr, (F + 3) / 4, stage_ids, count, capacity, staging,
+                                                                            staging_pitch);
+  return gs::launch_check("halo_fetch_kernel");
+}
+
 int32_t gs_gather_mean_sharded(const gs_sharded_table* table_host, int32_t dtype, int32_t F, int64_t pitch,
                                const gs_segment* segments_host, int32_t n_segments, int32_t include_self,
-                               int32_t ids_are_locators, void* out_self, void* out_mean, int64_t out_pitch, void* stream) {
+                               int32_t ids_are_locators, const void* staging, void* out_self, void* out_mean,
+                               int64_t out_pitch, void* stream) {
   GS_REQUIRE(dtype == GS_F32, "gs_gather_mean_sharded: only GS_F32 (dtype=%d)", dtype);
   GS_REQUIRE(n_segments >= 0 && n_segments <= GS_MAX_SEGMENTS && (segments_host || n_segments == 0),
              "gs_gather_mean_sharded: bad segments");
   gs::ShardRows sr;
   int32_t rc = fill_shard_tab(table_host, sr, pitch, "gs_gather_mean_sharded");
   if (rc != GS_OK) return rc;
-  sr.locators = ids_are_locators ? 1 : 0;
+  GS_REQUIRE(ids_are_locators >= 0 && ids_are_locators <= 2 && (ids_are_locators != 2 || staging != nullptr),
+             "gs_gather_mean_sharded: ids_are_locators = 2 needs the staging buffer");
+  sr.locators = ids_are_locators;
+  sr.staging = (const float*)staging;
   gs::SegTable tab;
   memset(&tab, 0, sizeof(tab));
   tab.n_segments = n_segments;

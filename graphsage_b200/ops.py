@@ -268,10 +268,44 @@ def _gather_mean_sharded(src, segments, include_self, want_self, out_pitch, out_
         out_mean = torch.empty((rows, out_pitch), dtype=torch.float32, device=src.device)
     if want_self and out_self is None:
         out_self = torch.empty((rows, out_pitch), dtype=torch.float32, device=src.device)
-    locators = 0
-    if getattr(src, "remap", None) is not None and any(s.self_ids is not None or s.neigh_ids is not None for s in segments):
-        # replicas: resolve every id list once (one pass per distinct tensor; hop-1 ids are self ids of one segment and
-        # neighbour ids of another) so the gather kernel's issue path has no table lookup
+    locators, staging = 0, None
+    by_ids = any(s.self_ids is not None or s.neigh_ids is not None for s in segments)
+    if by_ids and src.world > 1 and getattr(src, "stage_halo", True):
+        # halo staging: every remote row of the step crosses NVLink once (claim -> fetch -> translate), then the gather
+        # reads local memory only.  All buffers are per call: under CUDA-graph capture they live in the graph's pool.
+        lists, order = {}, []
+        for s in segments:
+            if (s.self_ids is None) != (s.neigh_ids is None):
+                raise ValueError("a segment over a sharded table must address self and neighbours the same way")
+            for t in (s.self_ids, s.neigh_ids):
+                key = (t.data_ptr(), t.numel())
+                if key not in lists:
+                    lists[key] = t
+                    order.append(key)
+        capacity = sum(lists[k].numel() for k in order)
+        dev = src.device
+        claim = torch.empty((src.shape[0],), dtype=torch.int32, device=dev)
+        count = torch.empty((1,), dtype=torch.int32, device=dev)
+        stage_ids = torch.empty((capacity,), dtype=torch.int32, device=dev)
+        staging = torch.empty((capacity, src.pitch), dtype=torch.float32, device=dev)
+        check(lib().gs_halo_begin(ptr(claim), src.shape[0], ptr(count), stream_ptr()))
+        for k in order:
+            check(lib().gs_halo_claim(src.c_table(), ptr(lists[k]), lists[k].numel(), ptr(claim), ptr(count), ptr(stage_ids),
+                                      capacity, stream_ptr()))
+        check(lib().gs_halo_fetch(src.c_table(), F, src.pitch, ptr(stage_ids), ptr(count), capacity, ptr(staging), src.pitch,
+                                  stream_ptr()))
+        locs = {}
+        for k in order:
+            locs[k] = torch.empty_like(lists[k])
+            check(lib().gs_halo_translate(src.c_table(), ptr(lists[k]), lists[k].numel(), ptr(claim), ptr(locs[k]), stream_ptr()))
+        _launched(2 * len(order) + 1)
+        segments = [Seg(s.n, s.k, locs[(s.self_ids.data_ptr(), s.self_ids.numel())],
+                        locs[(s.neigh_ids.data_ptr(), s.neigh_ids.numel())], s.self_row0, s.neigh_row0, s.out_row0)
+                    for s in segments]
+        locators = 2
+    elif by_ids and getattr(src, "remap", None) is not None:
+        # replicas, no staging: resolve every id list once (one pass per distinct tensor; hop-1 ids are self ids of one
+        # segment and neighbour ids of another) so the gather kernel's issue path has no table lookup
         done, segs = {}, []
 
         def tr(t):
@@ -290,8 +324,8 @@ def _gather_mean_sharded(src, segments, include_self, want_self, out_pitch, out_
     arr = (Segment * max(len(segments), 1))(*[s.c_struct() for s in segments])
     ev = _probe("gather_mean/%d" % rows)
     check(lib().gs_gather_mean_sharded(src.c_table(), _lib.GS_F32, F, src.pitch, arr, len(segments),
-                                       int(bool(include_self)), locators, ptr(out_self) if want_self else 0, ptr(out_mean),
-                                       out_pitch, stream_ptr()))
+                                       int(bool(include_self)), locators, ptr(staging), ptr(out_self) if want_self else 0,
+                                       ptr(out_mean), out_pitch, stream_ptr()))
     _launched(1 if rows else 0, ev)
     return (out_self if want_self else None), out_mean
 

@@ -58,9 +58,9 @@ def owner_of(ids, n_nodes, world, row_start=None):
 
 
 def default_cache_rows(n_nodes, world):
-    """Replica budget used by bench.py when none is given: one eighth of the table per GPU, whatever the GPU count
-    (at 8 GPUs a GPU then holds its own eighth plus as many replica rows)."""
-    return (int(n_nodes) + 7) // 8 if world > 1 else 0
+    """Replica budget used by bench.py when none is given: a quarter of the table per GPU, whatever the GPU count
+    (at 8 GPUs a GPU then holds its own eighth plus twice as many replica rows: 3/8 of the table)."""
+    return (int(n_nodes) + 3) // 4 if world > 1 else 0
 
 
 def hot_remote_rows(adj, n_nodes, world, rank, n_rows, row_start=None):
@@ -236,6 +236,8 @@ class ShardedFeatures(object):
                 raise ValueError("replica_ids must be sorted, unique, in range and not owned by this rank")
         self.replica_ids = rep_ids
         self.shape = (self.n_nodes + 1, F)
+        import os
+        self.stage_halo = os.environ.get("GS_HALO_STAGING", "0") == "1"   # opt-in: fetch every remote row of a step once (ops._gather_mean_sharded); measured slower at 2 GPUs
         self.pitch = pad_cols(F)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         rows_total = n_local + 1 + len(rep_ids)

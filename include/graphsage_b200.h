@@ -181,11 +181,26 @@ typedef struct {
   const int32_t* remap;                  /* device, [n_global_rows] or NULL (see above) */
 } gs_sharded_table;
 
-/* ids_are_locators != 0: the segments' id lists were translated by gs_translate_ids (below) */
+/* ids_are_locators: 0 = global ids; 1 = gs_translate_ids locators; 2 = gs_halo_translate locators (negative values index
+ * `staging`, this step's halo rows fetched by gs_halo_fetch; staging has the table's pitch) */
 int32_t gs_gather_mean_sharded(const gs_sharded_table* table_host, int32_t dtype, int32_t F, int64_t pitch,
                                const gs_segment* segments_host, int32_t n_segments, int32_t include_self,
-                               int32_t ids_are_locators, void* out_self, void* out_mean, int64_t out_pitch,
-                               void* stream);
+                               int32_t ids_are_locators, const void* staging, void* out_self, void* out_mean,
+                               int64_t out_pitch, void* stream);
+/* Halo staging - every remote row a step needs crosses NVLink ONCE (a frontier repeats remote nodes; peer reads bypass the
+ * local L2).  Per step:  gs_halo_begin (claim[] = -1, *count = 0)  ->  gs_halo_claim for every id list (first sighting of a
+ * remote id takes the next staging slot; stage_ids[slot] = id)  ->  gs_halo_fetch (rows of stage_ids[0 .. *count) from their
+ * owners into staging[slot])  ->  gs_halo_translate for every id list (out = row of this GPU's own buffer when the row is
+ * held locally, else -(slot) - 1)  ->  gs_gather_mean_sharded(..., ids_are_locators = 2, staging).
+ * claim: int32 [n_global_rows]; count: int32 [1]; stage_ids: int32 [capacity]; staging: float [capacity, staging_pitch];
+ * capacity >= the number of ids claimed (the sum of the lists' lengths always suffices). */
+int32_t gs_halo_begin(int32_t* claim, int64_t n_global_rows, int32_t* count, void* stream);
+int32_t gs_halo_claim(const gs_sharded_table* table_host, const int32_t* ids, int64_t n, int32_t* claim, int32_t* count,
+                      int32_t* stage_ids, int64_t capacity, void* stream);
+int32_t gs_halo_fetch(const gs_sharded_table* table_host, int32_t F, int64_t pitch, const int32_t* stage_ids,
+                      const int32_t* count, int64_t capacity, float* staging, int64_t staging_pitch, void* stream);
+int32_t gs_halo_translate(const gs_sharded_table* table_host, const int32_t* ids, int64_t n, const int32_t* claim,
+                          int32_t* out, void* stream);
 /* ids -> locators for a table with replicas (remap != NULL): out[i] = remap[ids[i]] (a row index inside this GPU's own
  * buffer) when the row is held locally - own rows, replicas, the zero row for ids outside [0, N) -, else -(ids[i]) - 1.
  * One cheap, fully parallel pass per id list; the gather kernel then needs no table lookup on its copy-issue path. */

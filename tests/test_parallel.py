@@ -179,6 +179,7 @@ def _gpu_worker(rank, world, port, q):
         outs = {}
         for kind, concat, dim in (("mean", True, 128), ("gcn", False, 256), ("maxpool", True, 32)):
             res = []
+            shard.stage_halo = kind != "gcn"               # both partitioned data paths: halo staging / direct peer copies
             for table in (shard, full):
                 gs.inits.manual_seed(7, dev)
                 sampler = gs.UniformNeighborSampler(adj_dev, seed=123)
