@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--math", default=os.environ.get("GS_MATH", "tf32x3"),
                     help="tf32x3 (tcgen05, fp32-grade: meets the 1e-4 parity bar) | fp32 (CUDA cores) | tf32 | bf16")
     ap.add_argument("--cpu-batches", type=int, default=12)
-    ap.add_argument("--depth", type=int, default=int(os.environ.get("GS_PIPE_DEPTH", "3")),
+    ap.add_argument("--depth", type=int, default=int(os.environ.get("GS_PIPE_DEPTH", "4")),
                     help="graph runners / compute streams alternating in the pipelined front end")
     ap.add_argument("--no-partitioned", action="store_true", help="skip the node-partitioned measurement at N > 1")
     ap.add_argument("--repeats", type=int, default=0,

@@ -78,6 +78,11 @@ _SIGNATURES = {
     "gs_sage_gemm_pack": (c_i32, [ctypes.POINTER(GemmPart), c_i32, c_i32, c_vp, c_vp]),
     "gs_sage_gemm_prepacked": (c_i32, [c_i64, ctypes.POINTER(GemmPart), c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_i64,
                                        c_vp, c_vp]),
+    "gs_gather_mean_img_bytes": (c_i64, [c_i64, c_i32, c_i32]),
+    "gs_gather_mean_img": (c_i32, [c_vp, c_i64, ctypes.POINTER(ShardedTable), c_i32, c_vp, c_i32, c_i64, ctypes.POINTER(Segment),
+                                   c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "gs_sage_gemm_img": (c_i32, [c_i64, ctypes.POINTER(GemmPart), c_i32, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_i32,
+                                 c_vp]),
     "gs_sage_layer_small": (c_i32, [c_vp, c_i64, c_i32, c_i64, ctypes.POINTER(Segment), c_i32, ctypes.POINTER(GemmPart),
                                     c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp, c_u64, c_vp]),
     "gs_maxpool_mlp_workspace_bytes": (c_i64, [c_i32, c_i32]),
@@ -89,6 +94,7 @@ _SIGNATURES = {
     "gs_pipeline_step": (c_i32, [c_vp, c_vp, c_i64, ctypes.POINTER(c_vp), c_i32, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
                                  c_vp, c_vp]),
     "gs_l2_normalize_rows": (c_i32, [c_vp, c_i64, c_i32, c_i64, c_vp]),
+    "gs_bump_counter": (c_i32, [c_vp, c_u64, c_vp]),
 }
 
 _lib = None

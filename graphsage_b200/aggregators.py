@@ -33,7 +33,29 @@ def _dense_segment(n, k):
     return [ops.make_segment(n, k)]
 
 
+USE_GEMM_IMAGES = [False]     # opt-in: tf32x3 layers hand the gathered rows to the GEMM as tensor-core tile images
+                              # (ops.gather_mean_images + ops.sage_gemm_img; bit-identical results).  Measured on the bench step:
+                              # the GEMM's A side becomes one bulk copy per K-block, but the gather - the critical kernel -
+                              # writes hi + lo images of both parts (55 MB instead of 27 MB): 59.3 us instead of 55.4, and the
+                              # pipelined step went from 74.1 to 76.3 us.  Kept off.
+
+
 class _SageAggregator(Layer):
+    def _image_layer(self, src, segments, parts, combine, include_self, want_self):
+        """gather + mean -> tile images -> tcgen05 GEMM (tf32x3); None when the image form does not apply."""
+        code, post = act_code(self.act)
+        if not USE_GEMM_IMAGES[0] or self.math != ops.MATH_TF32X3 or post is not None or self.dropout \
+                or any(K != src.shape[1] for (_, K, _) in parts):
+            return None
+        res = ops.gather_mean_images(src, segments, include_self=include_self, want_self=want_self)
+        if res is None:
+            return None
+        images, rows = res
+        if getattr(self, "_packed", None) is None:
+            self._packed = ops.PackedWeights()
+        return ops.sage_gemm_img(rows, images, parts, combine=combine, bias=self.vars.get("bias"), act=code,
+                                 packed=self._packed)
+
     def _finish(self, parts, combine):
         code, post = act_code(self.act)
         if getattr(self, "_packed", None) is None:
@@ -106,6 +128,11 @@ class MeanAggregator(_SageAggregator):
                               self._combine(), False, final)
         if y is not None:
             return y
+        y = self._image_layer(src, segments, [(None, self.input_dim, self.vars["self_weights"]),
+                                              (None, self.neigh_input_dim, self.vars["neigh_weights"])],
+                              self._combine(), False, True)
+        if y is not None:
+            return y
         xs, xm = ops.gather_mean(src, segments, want_self=True)
         return self._finish([(xs, self.input_dim, self.vars["self_weights"]),
                              (xm, self.neigh_input_dim, self.vars["neigh_weights"])], self._combine())
@@ -149,6 +176,9 @@ class GCNAggregator(_SageAggregator):
             raise NotImplementedError("dropout > 0 uses the dense call path")
         y = self._small_layer(src, segments, [(None, self.neigh_input_dim, self.vars["weights"])], ops.COMBINE_ADD, True,
                               final)
+        if y is not None:
+            return y
+        y = self._image_layer(src, segments, [(None, self.neigh_input_dim, self.vars["weights"])], ops.COMBINE_ADD, True, False)
         if y is not None:
             return y
         _, means = ops.gather_mean(src, segments, include_self=True, want_self=False)

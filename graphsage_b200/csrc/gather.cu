@@ -249,12 +249,38 @@ struct ShardRows {
 // ------------------------------------------------------------------------------------------
 constexpr int kGroupRows = 13;
 
+// A-operand images for the tcgen05 GEMM that follows (gs_sage_gemm_img, tf32x3): instead of (or besides) the fp32 rows,
+// the kernel writes each result row already SPLIT into tf32 hi / lo and laid out as the UMMA K-major SWIZZLE_128B tile
+// images the GEMM multiplies - part p (0 = self rows, 1 = mean rows), 128-row tile mt, 32-column K-block kb:
+//   img + ((((p * n_mtiles + mt) * kblocks + kb) * 2 + hl) * 16 KB) + sw128_off(row % 128, chunk),  hl = 0 hi / 1 lo,
+// so the GEMM's A operand is one 32 KB bulk copy per K-block (no producer warps, no register round trip, no proxy fence).
+struct GatherImg {
+  unsigned char* base;          // NULL: no images
+  int32_t kblocks, n_mtiles;
+  int32_t want_self;            // part 0 present (Mean); 0: only the mean part (GCN) at p = 0
+};
+
+__device__ __forceinline__ void gather_img_store(const GatherImg& im, int part, int64_t orow, int c, float4 v) {
+  const int kb = c >> 3, chunk = c & 7;
+  const int64_t mt = orow >> 7;
+  const int r = (int)(orow & 127);
+  unsigned char* dst = im.base + ((((int64_t)part * im.n_mtiles + mt) * im.kblocks + kb) * 2) * 16384 +
+                       (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
+  uint4 hi, lo;
+  hi.x = __float_as_uint(v.x) & 0xFFFFE000u; hi.y = __float_as_uint(v.y) & 0xFFFFE000u;
+  hi.z = __float_as_uint(v.z) & 0xFFFFE000u; hi.w = __float_as_uint(v.w) & 0xFFFFE000u;
+  lo.x = __float_as_uint(v.x - __uint_as_float(hi.x)) & 0xFFFFE000u; lo.y = __float_as_uint(v.y - __uint_as_float(hi.y)) & 0xFFFFE000u;
+  lo.z = __float_as_uint(v.z - __uint_as_float(hi.z)) & 0xFFFFE000u; lo.w = __float_as_uint(v.w - __uint_as_float(hi.w)) & 0xFFFFE000u;
+  *reinterpret_cast<uint4*>(dst) = hi;
+  *reinterpret_cast<uint4*>(dst + 16384) = lo;
+}
+
 template <class Rows>
 __global__ void __launch_bounds__(192) gather_mean_tma2_kernel(const __grid_constant__ Rows rows_of, int F,
                                                                const __grid_constant__ SegTable tab,
                                                                int include_self, float* __restrict__ out_self,
                                                                float* __restrict__ out_mean, int64_t out_pitch,
-                                                               int row_bytes) {
+                                                               int row_bytes, const __grid_constant__ GatherImg img) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar[2];
   if (threadIdx.x == 0) {
@@ -327,12 +353,13 @@ __global__ void __launch_bounds__(192) gather_mean_tma2_kernel(const __grid_cons
     }
     if (last) {
       const int64_t orow = sg.out_row0 + i;
+      const int ncol_img = img.base ? img.kblocks * 8 : 0;          // images are whole K-blocks: zero chunks past the row
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int c = threadIdx.x + q * blockDim.x;
-        if (c < ncol4) {
+        if (c < ncol4 || c < ncol_img) {
           float4 a = make_float4(0.f, 0.f, 0.f, 0.f), sv = a;
-          if (c * 4 < F) {
+          if (c < ncol4 && c * 4 < F) {
             a = acc[q];
             sv = rows[(cnt - 1) * row_f4 + c];
             const float div = (float)(k + (include_self ? 1 : 0));
@@ -341,9 +368,15 @@ __global__ void __launch_bounds__(192) gather_mean_tma2_kernel(const __grid_cons
             a = mask_tail(a, c * 4, F);
             sv = mask_tail(sv, c * 4, F);
           }
-          reinterpret_cast<float4*>(out_mean + orow * out_pitch)[c] = a;
-          if (out_self) reinterpret_cast<float4*>(out_self + orow * out_pitch)[c] = sv;
-          acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c < ncol4) {
+            if (out_mean) reinterpret_cast<float4*>(out_mean + orow * out_pitch)[c] = a;
+            if (out_self) reinterpret_cast<float4*>(out_self + orow * out_pitch)[c] = sv;
+          }
+          if (c < ncol_img) {
+            if (img.want_self) gather_img_store(img, 0, orow, c, sv);
+            gather_img_store(img, img.want_self ? 1 : 0, orow, c, a);
+          }
+          if (c < ncol4) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       r += gridDim.x;
@@ -428,23 +461,74 @@ __global__ void __launch_bounds__(256) gather_rows_to_f32_kernel(const T* __rest
   }
 }
 
+// the same for bf16 rows that are 16-byte multiples (pitch % 8 == 0, 16-byte aligned table and output, out_pitch % 8 == 0):
+// a lane converts 8 values per step (one 128-bit load, two 128-bit stores)
+__global__ void __launch_bounds__(256) gather_rows_bf16_to_f32_vec_kernel(const uint16_t* __restrict__ src, int64_t n_rows, int F,
+                                                                          int64_t pitch, const int32_t* __restrict__ ids,
+                                                                          int64_t row0, int64_t n, float* __restrict__ out,
+                                                                          int64_t out_pitch) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int chunks = (int)(out_pitch >> 3);
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const int64_t id = clamp_row(ids ? (int64_t)ids[i] : row0 + i, n_rows);
+    const uint4* rp = reinterpret_cast<const uint4*>(src + id * pitch);
+    float4* op = reinterpret_cast<float4*>(out + i * out_pitch);
+    for (int c = lane; c < chunks; c += 32) {
+      uint4 u = make_uint4(0u, 0u, 0u, 0u);
+      if (c * 8 < F) u = __ldg(rp + c);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v[2 * e] = (c * 8 + 2 * e < F) ? __uint_as_float(w[e] << 16) : 0.f;
+        v[2 * e + 1] = (c * 8 + 2 * e + 1 < F) ? __uint_as_float(w[e] & 0xffff0000u) : 0.f;
+      }
+      op[2 * c] = make_float4(v[0], v[1], v[2], v[3]);
+      op[2 * c + 1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t f32_to_bf16_rne(float x) {
+  const uint32_t u = __float_as_uint(x);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (u >> 16) | 0x40u;          // NaN stays NaN
+  return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
+}
+
 // fp32 [n, F] -> bf16 [n, out_pitch] (round to nearest even, pad columns zeroed): the layer-(l+1) source of the
-// bf16 max-pool path
+// bf16 max-pool path.  A thread produces 8 consecutive outputs (one 128-bit store); out_pitch % 8 == 0.
 __global__ void __launch_bounds__(256) cast_rows_bf16_kernel(const float* __restrict__ x, int64_t n, int F, int64_t ldx,
                                                              uint16_t* __restrict__ out, int64_t out_pitch) {
+  const int chunks = (int)(out_pitch >> 3);
+  const int64_t total = n * chunks;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = q / chunks;
+    const int c = (int)(q - i * chunks) * 8;
+    const float* xp = x + i * ldx + c;
+    uint32_t h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h[e] = (c + e < F) ? f32_to_bf16_rne(xp[e]) : 0u;
+    uint4 o;
+    o.x = h[0] | (h[1] << 16); o.y = h[2] | (h[3] << 16); o.z = h[4] | (h[5] << 16); o.w = h[6] | (h[7] << 16);
+    *reinterpret_cast<uint4*>(out + i * out_pitch + c) = o;
+  }
+}
+
+// any out_pitch (scalar stores)
+__global__ void __launch_bounds__(256) cast_rows_bf16_scalar_kernel(const float* __restrict__ x, int64_t n, int F, int64_t ldx,
+                                                                    uint16_t* __restrict__ out, int64_t out_pitch) {
   const int64_t total = n * out_pitch;
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = q / out_pitch;
     const int c = (int)(q - i * out_pitch);
-    uint16_t h = 0;
-    if (c < F) {
-      const uint32_t u = __float_as_uint(x[i * ldx + c]);
-      if ((u & 0x7fffffffu) > 0x7f800000u) h = (uint16_t)((u >> 16) | 0x40u);          // NaN stays NaN
-      else h = (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
-    }
-    out[q] = h;
+    out[q] = c < F ? (uint16_t)f32_to_bf16_rne(x[i * ldx + c]) : (uint16_t)0;
   }
 }
+
+// *counter += inc on the stream (the samplers' device-side call counter, advanced once per step)
+__global__ void bump_counter_kernel(unsigned long long* counter, unsigned long long inc) { *counter += inc; }
 
 __global__ void __launch_bounds__(256) segment_max_kernel(const float* __restrict__ x, int64_t n, int k, int C,
                                                           int64_t ldx, float* __restrict__ out, int64_t ldo) {
@@ -638,6 +722,33 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 
 }  // namespace gs
 
+
+namespace gs {
+// launch of the grouped double-buffered bulk-copy gather (dense or sharded resolver), with or without A-operand images
+template <class Rows>
+static int32_t launch_gather_tma2(const Rows& rows_of, int F, const SegTable& tab, int include_self, float* out_self, float* out_mean,
+                                  int64_t out_pitch, const GatherImg& img, cudaStream_t st) {
+  const int32_t rc_attr = ensure_dyn_smem((const void*)gather_mean_tma2_kernel<Rows>, 200 * 1024);
+  if (rc_attr != GS_OK) return rc_attr;
+  const int ncol4 = (int)(out_pitch / 4);
+  const int row_bytes = ((F + 3) / 4) * 16;
+  const size_t smem2 = (size_t)2 * kGroupRows * row_bytes;
+  int threads = ((ncol4 + 31) / 32) * 32;
+  if (threads > 160) threads = 160;
+  if (threads < 32) threads = 32;
+  int per_sm = (int)((224 * 1024) / (smem2 + 1024));
+  if (per_sm < 1) per_sm = 1;
+  int lim = tuning("gather_ctas_per_sm", 8);
+  if (per_sm > lim) per_sm = lim;
+  int64_t blocks = tab.total_rows;
+  int64_t cap = (int64_t)sm_count() * per_sm;
+  if (blocks > cap) blocks = cap;
+  gather_mean_tma2_kernel<Rows><<<(unsigned)blocks, threads, smem2, st>>>(rows_of, F, tab, include_self, out_self, out_mean,
+                                                                          out_pitch, row_bytes, img);
+  return launch_check("gather_mean_tma2_kernel");
+}
+}  // namespace gs
+
 extern "C" {
 
 int32_t gs_gather_rows(const void* feats, int32_t dtype, int64_t n_rows, int32_t F, int64_t pitch, const int32_t* ids,
@@ -718,25 +829,10 @@ int32_t gs_gather_mean(const void* src, int32_t dtype, int64_t n_src_rows, int32
   const size_t smem = (size_t)row_bytes * (kmax + 1);
   const int variant = gs::tuning("gather_variant", 2);   // 2: grouped double-buffered TMA (default), 1: whole-node TMA, 0: LDG
   if (variant == 2 && ncol4 <= 2 * 160) {
-    {
-      const int32_t rc_attr = gs::ensure_dyn_smem((const void*)gs::gather_mean_tma2_kernel<gs::DenseRows>, 200 * 1024);
-      if (rc_attr != GS_OK) return rc_attr;
-    }
-    const size_t smem2 = (size_t)2 * gs::kGroupRows * row_bytes;
-    int threads = ((ncol4 + 31) / 32) * 32;
-    if (threads > 160) threads = 160;
-    if (threads < 32) threads = 32;
-    int per_sm = (int)((224 * 1024) / (smem2 + 1024));
-    if (per_sm < 1) per_sm = 1;
-    int lim = gs::tuning("gather_ctas_per_sm", 8);
-    if (per_sm > lim) per_sm = lim;
-    int64_t blocks = tab.total_rows;
-    int64_t cap = (int64_t)gs::sm_count() * per_sm;
-    if (blocks > cap) blocks = cap;
     const gs::DenseRows rows_of{fsrc, n_src_rows, pitch};
-    gs::gather_mean_tma2_kernel<gs::DenseRows><<<(unsigned)blocks, threads, smem2, st>>>(
-        rows_of, F, tab, include_self, (float*)out_self, (float*)out_mean, out_pitch, row_bytes);
-    return gs::launch_check("gather_mean_tma2_kernel");
+    gs::GatherImg img;
+    memset(&img, 0, sizeof(img));
+    return gs::launch_gather_tma2(rows_of, F, tab, include_self, (float*)out_self, (float*)out_mean, out_pitch, img, st);
   }
   if (variant >= 1 && smem <= 200 * 1024) {
     {
@@ -781,6 +877,9 @@ int32_t gs_gather_rows_f32(const void* feats, int32_t dtype, int64_t n_rows, int
   if (dtype == GS_F32)
     gs::gather_rows_to_f32_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         (const float*)feats, n_rows, F, pitch, ids, row0, n, out, out_pitch);
+  else if (pitch % 8 == 0 && out_pitch % 8 == 0 && gs::aligned16(feats) && gs::aligned16(out) && out_pitch <= pitch)
+    gs::gather_rows_bf16_to_f32_vec_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const uint16_t*)feats, n_rows, F, pitch, ids, row0, n, out, out_pitch);
   else
     gs::gather_rows_to_f32_kernel<uint16_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         (const uint16_t*)feats, n_rows, F, pitch, ids, row0, n, out, out_pitch);
@@ -792,11 +891,22 @@ int32_t gs_cast_rows_bf16(const float* x, int64_t n, int32_t F, int64_t ldx, voi
   GS_REQUIRE(n >= 0 && F >= 0 && ldx >= F && out_pitch >= F, "gs_cast_rows_bf16: bad sizes");
   if (n == 0 || out_pitch == 0) return GS_OK;
   GS_REQUIRE(x && out_bf16, "gs_cast_rows_bf16: NULL pointer");
-  int64_t blocks = (n * out_pitch + 255) / 256;
+  const bool vec = out_pitch % 8 == 0 && gs::aligned16(out_bf16) && ldx >= ((F + 7) / 8) * 8;
+  int64_t blocks = ((vec ? n * (out_pitch / 8) : n * out_pitch) + 255) / 256;
   int64_t cap = (int64_t)gs::sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  gs::cast_rows_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, F, ldx, (uint16_t*)out_bf16, out_pitch);
+  if (vec)
+    gs::cast_rows_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, F, ldx, (uint16_t*)out_bf16, out_pitch);
+  else
+    gs::cast_rows_bf16_scalar_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, F, ldx, (uint16_t*)out_bf16,
+                                                                                         out_pitch);
   return gs::launch_check("cast_rows_bf16_kernel");
+}
+
+int32_t gs_bump_counter(uint64_t* counter_dev, uint64_t inc, void* stream) {
+  GS_REQUIRE(counter_dev != nullptr, "gs_bump_counter: NULL counter");
+  gs::bump_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)counter_dev, (unsigned long long)inc);
+  return gs::launch_check("bump_counter_kernel");
 }
 
 int32_t gs_segment_max(const float* x, int64_t n, int32_t k, int32_t C, int64_t ldx, float* out, int64_t ldo,
@@ -868,6 +978,57 @@ int32_t gs_translate_ids(const gs_sharded_table* table_host, const int32_t* ids,
   gs::translate_ids_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(table_host->remap, table_host->n_global_rows,
                                                                                 (int32_t)table_host->zero_row, ids, n, out);
   return gs::launch_check("translate_ids_kernel");
+}
+
+int64_t gs_gather_mean_img_bytes(int64_t rows, int32_t F, int32_t want_self) {
+  if (rows < 0 || F < 1) return -1;
+  const int64_t n_mtiles = (rows + 127) / 128, kblocks = (F + 31) / 32;
+  return (want_self ? 2 : 1) * n_mtiles * kblocks * 2 * 16384;
+}
+
+int32_t gs_gather_mean_img(const void* src, int64_t n_src_rows, const gs_sharded_table* table_host, int32_t ids_are_locators,
+                           const void* staging, int32_t F, int64_t pitch, const gs_segment* segments_host, int32_t n_segments,
+                           int32_t include_self, int32_t want_self, void* images, void* stream) {
+  GS_REQUIRE((src != nullptr) != (table_host != nullptr), "gs_gather_mean_img: pass either a dense table or a sharded one");
+  GS_REQUIRE(n_segments >= 0 && n_segments <= GS_MAX_SEGMENTS && (segments_host || n_segments == 0),
+             "gs_gather_mean_img: bad segments");
+  gs::SegTable tab;
+  memset(&tab, 0, sizeof(tab));
+  tab.n_segments = n_segments;
+  int64_t rows = 0;
+  for (int s = 0; s < n_segments; ++s) {
+    tab.s[s] = segments_host[s];
+    GS_REQUIRE(tab.s[s].n >= 0 && tab.s[s].k >= 1, "gs_gather_mean_img: segment %d has n=%lld k=%d", s, (long long)tab.s[s].n,
+               tab.s[s].k);
+    tab.total_rows += tab.s[s].n;
+    if (tab.s[s].out_row0 + tab.s[s].n > rows) rows = tab.s[s].out_row0 + tab.s[s].n;
+  }
+  if (tab.total_rows == 0) return GS_OK;
+  GS_REQUIRE(images && (reinterpret_cast<uintptr_t>(images) & 1023u) == 0, "gs_gather_mean_img: images must be 1024-byte aligned");
+  const int64_t out_pitch = ((int64_t)F + 7) / 8 * 8;
+  const int ncol4 = (int)(out_pitch / 4);
+  if (ncol4 > 2 * 160 || F < 1 || pitch % 4 != 0 || pitch < ((F + 3) / 4) * 4 || gs::tuning("gather_variant", 2) != 2) {
+    gs::set_error("gs_gather_mean_img: needs F <= 1280, 16-byte row pitch and the bulk-copy gather (F=%d pitch=%lld)", F, (long long)pitch);
+    return GS_ERR_UNSUPPORTED;
+  }
+  gs::GatherImg img;
+  img.base = (unsigned char*)images;
+  img.kblocks = (F + 31) / 32;
+  img.n_mtiles = (int32_t)((rows + 127) / 128);
+  img.want_self = want_self ? 1 : 0;
+  if (src) {
+    GS_REQUIRE(gs::aligned16(src) && n_src_rows > 0, "gs_gather_mean_img: table must be 16-byte aligned");
+    const gs::DenseRows rows_of{(const float*)src, n_src_rows, pitch};
+    return gs::launch_gather_tma2(rows_of, F, tab, include_self, nullptr, nullptr, out_pitch, img, (cudaStream_t)stream);
+  }
+  gs::ShardRows sr;
+  int32_t rc = fill_shard_tab(table_host, sr, pitch, "gs_gather_mean_img");
+  if (rc != GS_OK) return rc;
+  GS_REQUIRE(ids_are_locators >= 0 && ids_are_locators <= 2 && (ids_are_locators != 2 || staging != nullptr),
+             "gs_gather_mean_img: ids_are_locators = 2 needs the staging buffer");
+  sr.locators = ids_are_locators;
+  sr.staging = (const float*)staging;
+  return gs::launch_gather_tma2(sr, F, tab, include_self, nullptr, nullptr, out_pitch, img, (cudaStream_t)stream);
 }
 
 int32_t gs_halo_begin(int32_t* claim, int64_t n_global_rows, int32_t* count, void* stream) {
@@ -953,24 +1114,13 @@ int32_t gs_gather_mean_sharded(const gs_sharded_table* table_host, int32_t dtype
                  F > 0 && pitch >= ((F + 3) / 4) * 4 && out_pitch >= F,
              "gs_gather_mean_sharded: bad output / pitch");
   const int ncol4 = (int)(out_pitch / 4);
-  const int row_bytes = ((F + 3) / 4) * 16;
   // default: the grouped double-buffered bulk-copy kernel of the dense table with peer-mapped row addresses - a
   // remote row is one cp.async.bulk over NVLink straight into this SM's shared memory (gather_variant=0: 128-bit loads)
   if (gs::tuning("gather_variant", 2) != 0 && ncol4 <= 2 * 160) {
-    const int32_t rc_attr = gs::ensure_dyn_smem((const void*)gs::gather_mean_tma2_kernel<gs::ShardRows>, 200 * 1024);
-    if (rc_attr != GS_OK) return rc_attr;
-    const size_t smem2 = (size_t)2 * gs::kGroupRows * row_bytes;
-    int threads = ((ncol4 + 31) / 32) * 32;
-    if (threads > 160) threads = 160;
-    if (threads < 32) threads = 32;
-    int per_sm = (int)((224 * 1024) / (smem2 + 1024));
-    if (per_sm < 1) per_sm = 1;
-    int64_t blocks = tab.total_rows;
-    int64_t cap = (int64_t)gs::sm_count() * per_sm;
-    if (blocks > cap) blocks = cap;
-    gs::gather_mean_tma2_kernel<gs::ShardRows><<<(unsigned)blocks, threads, smem2, (cudaStream_t)stream>>>(
-        sr, F, tab, include_self, (float*)out_self, (float*)out_mean, out_pitch, row_bytes);
-    return gs::launch_check("gather_mean_tma2_kernel<ShardRows>");
+    gs::GatherImg img;
+    memset(&img, 0, sizeof(img));
+    return gs::launch_gather_tma2(sr, F, tab, include_self, (float*)out_self, (float*)out_mean, out_pitch, img,
+                                  (cudaStream_t)stream);
   }
   int threads = ((ncol4 + 31) / 32) * 32;
   if (threads > 256) threads = 256;

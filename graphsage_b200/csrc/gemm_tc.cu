@@ -46,6 +46,9 @@ struct TcParams {
   int64_t ldo;
   int32_t tiles_n0;    // number of N tiles of part 0 (CONCAT tile -> part mapping)
   int32_t issue_elect; // 1: warp-uniform elect.sync issue (default), 0: one thread inside `if (lane == 0)`
+  const unsigned char* a_img;   // image form (sage_gemm_tc_img_kernel): A operands as tf32 hi/lo tile images (gs_gather_mean_img)
+  int32_t a_mtiles;             // 128-row tiles in the A images
+  int32_t a_part0;              // A-image part that feeds GEMM part 0 (GEMM part p reads A part a_part0 + p)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -444,6 +447,152 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sage_gemm_tc_kernel(const __gri
 }
 
 // ---------------------------------------------------------------------------------------------
+// Image form (tf32x3 only): the A operand arrives as the tf32 hi / lo UMMA tile images the fused gather wrote
+// (gs_gather_mean_img), so a K-block of A is ONE 32 KB bulk copy - no producer warps, no register round trip, no hi/lo
+// split here, no generic->async proxy fence.  Same arithmetic as sage_gemm_tc_kernel<0> (A_hi*B_hi + A_hi*B_lo +
+// A_lo*B_hi in that order, fp32 accumulate in TMEM): results are bit-identical to it.
+//   warp 0: A loader (bulk copies)   warp 1: B loader   warp 2: MMA issuer (+ TMEM alloc)   warps 4-7: epilogue
+// Three 32 KB stages per operand (192 KB): the ring covers the L2 -> shared latency, which the register-staged form could not.
+// ---------------------------------------------------------------------------------------------
+constexpr int TCI_THREADS = 256;
+constexpr int TCI_IMG = 2 * TC_TILE_BYTES;      // hi + lo image of one K-block
+constexpr int TCI_SA = 3, TCI_NB = 3;
+constexpr int TCI_SMEM = (TCI_SA + TCI_NB) * TCI_IMG + 1024;
+
+__global__ void __launch_bounds__(TCI_THREADS, 1) sage_gemm_tc_img_kernel(const __grid_constant__ TcParams prm,
+                                                                          const unsigned char* __restrict__ ws) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_a[TCI_SA], empty_a[TCI_SA], full_b[TCI_NB], empty_b[TCI_NB], accum_bar;
+  __shared__ uint32_t tmem_base_smem;
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* a_ring = smem;
+  unsigned char* b_ring = smem + TCI_SA * TCI_IMG;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int64_t m0 = (int64_t)blockIdx.x * TC_BM;
+  int part_lo = 0, part_hi = prm.n_parts, ntile = blockIdx.y, col_off = 0;
+  if (prm.combine == GS_COMBINE_CONCAT && prm.n_parts == 2) {
+    if ((int)blockIdx.y < prm.tiles_n0) part_hi = 1;
+    else { part_lo = 1; ntile = blockIdx.y - prm.tiles_n0; col_off = prm.p[0].N; }
+  }
+  const int N = prm.p[part_lo].N;
+  int total_it = 0;
+  for (int pi = part_lo; pi < part_hi; ++pi) total_it += prm.p[pi].kblocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TCI_SA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
+    for (int s = 0; s < TCI_NB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+    mbar_init(&accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&tmem_base_smem, TC_BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = tmem_base_smem;
+
+  if (warp == 0) {
+    // =============================== A loader ===============================
+    if (lane == 0) {
+      int it = 0;
+      for (int pi = part_lo; pi < part_hi; ++pi) {
+        const TcPart& P = prm.p[pi];
+        const unsigned char* base = prm.a_img + (((int64_t)(prm.a_part0 + pi) * prm.a_mtiles + blockIdx.x) * P.kblocks) * TCI_IMG;
+        for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
+          const int sa = it % TCI_SA;
+          mbar_wait(&empty_a[sa], ((uint32_t)(it / TCI_SA) & 1u) ^ 1u);
+          mbar_expect_tx(&full_a[sa], TCI_IMG);
+          bulk_g2s(a_ring + (size_t)sa * TCI_IMG, base + (int64_t)kb * TCI_IMG, TCI_IMG, &full_a[sa]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =============================== B loader ===============================
+    if (lane == 0) {
+      int it = 0;
+      for (int pi = part_lo; pi < part_hi; ++pi) {
+        const TcPart& P = prm.p[pi];
+        const unsigned char* base = ws + P.img_off + (int64_t)ntile * P.kblocks * TCI_IMG;
+        for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
+          const int sb = it % TCI_NB;
+          mbar_wait(&empty_b[sb], ((uint32_t)(it / TCI_NB) & 1u) ^ 1u);
+          mbar_expect_tx(&full_b[sb], TCI_IMG);
+          bulk_g2s(b_ring + (size_t)sb * TCI_IMG, base + (int64_t)kb * TCI_IMG, TCI_IMG, &full_b[sb]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    // =============================== MMA issuer ===============================
+    constexpr uint32_t idesc = make_idesc(2u, TC_BM, TC_BN);            // tf32 x tf32 -> fp32
+    for (int it = 0; it < total_it; ++it) {
+      const int sa = it % TCI_SA, sb = it % TCI_NB;
+      mbar_wait_uniform(&full_a[sa], (uint32_t)(it / TCI_SA) & 1u);
+      mbar_wait_uniform(&full_b[sb], (uint32_t)(it / TCI_NB) & 1u);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(a_ring + (size_t)sa * TCI_IMG), b_base = smem_u32(b_ring + (size_t)sb * TCI_IMG);
+      const uint64_t a_hi = make_smem_desc(a_base), b_hi = make_smem_desc(b_base);
+      const uint64_t a_lo = make_smem_desc(a_base + TC_TILE_BYTES), b_lo = make_smem_desc(b_base + TC_TILE_BYTES);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {                                     // four K = 8 steps per 32-column K-block
+        const uint64_t koff = (uint64_t)((k * 32) >> 4);
+        umma_ss_elect<false>(tmem_acc, a_hi + koff, b_hi + koff, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        umma_ss_elect<false>(tmem_acc, a_hi + koff, b_lo + koff, idesc, 1u);
+        umma_ss_elect<false>(tmem_acc, a_lo + koff, b_hi + koff, idesc, 1u);
+      }
+      umma_commit_elect(&empty_a[sa]);
+      umma_commit_elect(&empty_b[sb]);
+      if (it == total_it - 1) umma_commit_elect(&accum_bar);
+    }
+  } else if (warp >= 4) {
+    // =============================== epilogue ===============================
+    mbar_wait(&accum_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;                           // TMEM lane quarter of this warp
+    const int64_t grow = m0 + q * 32 + lane;
+#pragma unroll 1
+    for (int cb = 0; cb < 4; ++cb) {
+      const int col0 = cb * 32;
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, r);
+      tmem_ld_wait();
+      if (grow < prm.M) {
+        const int gn0 = ntile * TC_BN + col0;
+        float* dst = prm.out + grow * prm.ldo + col_off + gn0;
+        const bool vec = ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) && gn0 + 32 <= N;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            v[e] = __uint_as_float(r[j + e]);
+            if (prm.bias && gn0 + j + e < N) v[e] += prm.bias[col_off + gn0 + j + e];
+            if (prm.act == GS_ACT_RELU) v[e] = fmaxf(v[e], 0.f);
+          }
+          if (vec) {
+            *reinterpret_cast<float4*>(dst + j) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (gn0 + j + e < N) dst[j + e] = v[e];
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, TC_BN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 static int mode_of(int32_t math) { return math == GS_MATH_TF32X3 ? 0 : math == GS_MATH_TF32 ? 1 : 2; }
@@ -523,6 +672,30 @@ int32_t sage_gemm_tc_pack(const gs_gemm_part* parts, int32_t n_parts, int32_t ma
   if (mode == 0) return launch_pack<0>(prm, ws, st);
   if (mode == 1) return launch_pack<1>(prm, ws, st);
   return launch_pack<2>(prm, ws, st);
+}
+
+int32_t sage_gemm_tc_img(int64_t M, const gs_gemm_part* parts, int32_t n_parts, int32_t combine, const float* bias, int32_t act,
+                         float* out, int64_t ldo, const void* workspace, const void* a_images, int32_t a_part0,
+                         cudaStream_t st) {
+  GS_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 127u) == 0,
+             "gs_sage_gemm_img: packed weights missing or not 128-byte aligned");
+  GS_REQUIRE(a_images != nullptr && (reinterpret_cast<uintptr_t>(a_images) & 1023u) == 0,
+             "gs_sage_gemm_img: A images missing or not 1024-byte aligned");
+  TcParams prm;
+  fill_parts(prm, M, parts, n_parts, 0);
+  for (int i = 1; i < n_parts; ++i)
+    GS_REQUIRE(prm.p[i].K == prm.p[0].K, "gs_sage_gemm_img: every part must have the K of the gathered rows");
+  prm.combine = combine; prm.bias = bias; prm.act = act; prm.out = out; prm.ldo = ldo;
+  prm.a_img = (const unsigned char*)a_images;
+  prm.a_mtiles = (int32_t)((M + TC_BM - 1) / TC_BM);
+  prm.a_part0 = a_part0;
+  const int32_t rc_attr = ensure_dyn_smem((const void*)sage_gemm_tc_img_kernel, TCI_SMEM);
+  if (rc_attr != GS_OK) return rc_attr;
+  int tiles_n = prm.p[0].ntiles;
+  if (combine == GS_COMBINE_CONCAT && n_parts == 2) tiles_n += prm.p[1].ntiles;
+  dim3 grid((unsigned)prm.a_mtiles, (unsigned)tiles_n);
+  sage_gemm_tc_img_kernel<<<grid, TCI_THREADS, TCI_SMEM, st>>>(prm, (const unsigned char*)workspace);
+  return launch_check("sage_gemm_tc_img_kernel");
 }
 
 int32_t sage_gemm_tc(int64_t M, const gs_gemm_part* parts, int32_t n_parts, int32_t combine, const float* bias,

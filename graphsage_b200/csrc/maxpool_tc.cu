@@ -1981,18 +1981,22 @@ static int32_t pool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K,
     int64_t ctas_t = (int64_t)(gs::sm_count() / prm.n_slices) * prm.n_slices;   // a whole number of slice groups
     if (ctas_t < prm.n_slices) ctas_t = prm.n_slices;
     if (ctas_t > prm.n_tiles * prm.n_slices) ctas_t = prm.n_tiles * prm.n_slices;
-    if (nt == 128 && gs::tuning("k4_cluster", 1) == 1 && (prm.n_slices == 2 || prm.n_slices == 4 || prm.n_slices == 8) &&
-        prm.n_stages >= gs::MPC_PW) {
+    // k4_cluster: cluster size (2, 4 or 8 CTAs = that many hidden slices of one tile share their gathered rows); -1 = all
+    // hidden/128 slices of a tile; 0 = no clusters.  Default 2: pairs fill all 148 SMs (74 clusters), clusters of four only
+    // 132 (33 fit the GPCs): 111 us against 117 us at hop 2.
+    int cl = gs::tuning("k4_cluster", 2);
+    if (cl < 0 || cl > prm.n_slices) cl = prm.n_slices;
+    if (nt == 128 && (cl == 2 || cl == 4 || cl == 8) && prm.n_slices % cl == 0 && prm.n_stages >= gs::MPC_PW) {
       prm.n_stages -= prm.n_stages % gs::MPC_PW;         // a ring slot is always filled by the same producer warp
       CUtensorMap tmap;
       const int32_t rcm = make_table_tensor_map(&tmap, table_bf16, n_rows, K, pitch, 64);
       if (rcm != GS_OK) return rcm;
-      const void* fnc = prm.n_slices == 2   ? (const void*)gs::maxpool_mlp_tmemc_kernel<2>
-                        : prm.n_slices == 4 ? (const void*)gs::maxpool_mlp_tmemc_kernel<4>
-                                            : (const void*)gs::maxpool_mlp_tmemc_kernel<8>;
+      const void* fnc = cl == 2   ? (const void*)gs::maxpool_mlp_tmemc_kernel<2>
+                        : cl == 4 ? (const void*)gs::maxpool_mlp_tmemc_kernel<4>
+                                  : (const void*)gs::maxpool_mlp_tmemc_kernel<8>;
       const int32_t rcc = gs::ensure_dyn_smem(fnc, gs::MPW_SMEM);
       if (rcc != GS_OK) return rcc;
-      if (prm.n_slices == 8) GS_CUDA(cudaFuncSetAttribute(fnc, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
+
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof(cfg));
       cfg.gridDim = dim3((unsigned)ctas_t);              // a multiple of n_slices: whole clusters
@@ -2001,7 +2005,7 @@ static int32_t pool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K,
       cfg.stream = (cudaStream_t)stream;
       cudaLaunchAttribute attr;
       attr.id = cudaLaunchAttributeClusterDimension;
-      attr.val.clusterDim.x = (unsigned)prm.n_slices;
+      attr.val.clusterDim.x = (unsigned)cl;
       attr.val.clusterDim.y = 1;
       attr.val.clusterDim.z = 1;
       cfg.attrs = &attr;
@@ -2009,13 +2013,14 @@ static int32_t pool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K,
       // persistent clusters: launch only as many as can be resident at once (a GPC whose SM count is not a multiple of the
       // cluster size leaves SMs over, so 148 SMs do not always hold 148 / CL clusters)
       static int max_clusters[3] = {0, 0, 0};
-      int& mc = max_clusters[prm.n_slices == 2 ? 0 : prm.n_slices == 4 ? 1 : 2];
+      int& mc = max_clusters[cl == 2 ? 0 : cl == 4 ? 1 : 2];
       if (mc == 0) {
         int n = 0;
         GS_CUDA(cudaOccupancyMaxActiveClusters(&n, fnc, &cfg));
         mc = n > 0 ? n : 1;
       }
-      if ((int64_t)mc * prm.n_slices < ctas_t) cfg.gridDim = dim3((unsigned)(mc * prm.n_slices));
+      // (the grid stays a multiple of n_slices: every tile needs all its slices)
+      if ((int64_t)mc * cl < ctas_t) cfg.gridDim = dim3((unsigned)(((int64_t)mc * cl / prm.n_slices) * prm.n_slices));
       void* args[2] = {(void*)&prm, (void*)&tmap};
       GS_CUDA(cudaLaunchKernelExC(&cfg, fnc, args));
       return gs::launch_check("maxpool_mlp_tmemc_kernel");

@@ -203,7 +203,8 @@ class SampleAndAggregate(object):
         if normalize and not final.get("normalized"):
             out = ops.l2_normalize_rows_(out.contiguous())
         if final["bump"] is not None and not final.get("bumped"):
-            final["bump"][0].add_(final["bump"][1])
+            ops.check(ops.lib().gs_bump_counter(final["bump"][0].data_ptr(), int(final["bump"][1]), ops.stream_ptr()))
+            ops._launched(1)
         return out
 
 

@@ -591,7 +591,7 @@ def test_packed_weights_follow_weight_updates(gs):
     (3, 128, 64, 256, True),           # one group per tile
     (1000, 1, 602, 1024, True),        # k = 1 (max over a single row), "big" hidden
 ])
-@pytest.mark.parametrize("variant", ["tmem128c", "tmem128", "tmem128x2", "tmem256", "wide128_tma", "wide128_cpasync", "wide256_cpasync", "round1"])
+@pytest.mark.parametrize("variant", ["tmem128c", "tmem128c2", "tmem128", "tmem128x2", "tmem256", "wide128_tma", "wide128_cpasync", "wide256_cpasync", "round1"])
 def test_maxpool_mlp_fused_vs_reference(gs, case, variant):
     n_groups, k, K, hidden, use_ids = case
     if k > K4_VARIANTS[variant][2]:
@@ -600,12 +600,13 @@ def test_maxpool_mlp_fused_vs_reference(gs, case, variant):
     try:
         _maxpool_mlp_case(gs, n_groups, k, K, hidden, use_ids)
     finally:
-        _k4_select(gs, "tmem128c")
+        _k4_select(gs, "tmem128c2")
 
 
 # name -> (k4_kernel, k4_wide_producer, tile rows, k4_pipes, k4_cluster)
-K4_VARIANTS = {"tmem128c": (0, 1, 128, 1, 1),         # default: weights in tensor memory, the slices of a tile form a cluster,
-                                                      # rows gathered once per cluster by TMA gather4 multicast
+K4_VARIANTS = {"tmem128c2": (0, 1, 128, 1, 2),        # default: weights in tensor memory, PAIRS of a tile's hidden slices form a
+                                                      # cluster, rows gathered once per cluster by TMA gather4 multicast
+               "tmem128c": (0, 1, 128, 1, -1),        # clusters of all hidden/128 slices of a tile
                "tmem128": (0, 1, 128, 1, 0),          # one CTA per slice gathers its own rows (cp.async)
                "tmem128x2": (0, 1, 128, 2, 0),        # two producer->MMA chains per CTA
                "tmem256": (0, 1, 256, 1, 0),          # one chain, one 256-column accumulator
@@ -631,7 +632,7 @@ def test_maxpool_mlp_fused_wide_fanouts(gs):
              (900, 5, 64, 128), (333, 7, 33, 128), (260, 25, 512, 256), (260, 25, 513, 128), (1500, 25, 602, 128))
     wide = ((7, 200, 602, 128), (2, 256, 64, 256), (11, 129, 300, 128), (700, 9, 32, 128))
     try:
-        for name in ("tmem128c", "tmem128", "tmem128x2", "tmem256", "wide128_tma", "wide128_cpasync", "wide256_cpasync"):
+        for name in ("tmem128c", "tmem128c2", "tmem128", "tmem128x2", "tmem256", "wide128_tma", "wide128_cpasync", "wide256_cpasync"):
             _k4_select(gs, name)
             tile = K4_VARIANTS[name][2]
             for case in cases + (wide if tile == 256 else ()):
@@ -639,7 +640,7 @@ def test_maxpool_mlp_fused_wide_fanouts(gs):
             with pytest.raises(RuntimeError, match="k <= %d" % tile):
                 _maxpool_mlp_case(gs, 2, tile + 1, 64, 128, True)
     finally:
-        _k4_select(gs, "tmem128c")
+        _k4_select(gs, "tmem128c2")
 
 
 def _maxpool_mlp_case(gs, n_groups, k, K, hidden, use_ids):
@@ -833,3 +834,61 @@ def test_csr_sampled_model_vs_oracle(gs):
     aggs = [dict(type="mean", **{k: v.cpu().numpy() for k, v in a.vars.items()}) for a in m.aggregators]
     ref = oracle.l2_normalize(oracle.aggregate_khop([seeds, h1, h2], feats, [25, 10], [1, 10, 250], B, aggs, True))
     assert rel_err(out, ref) < TOL
+
+
+# ---------------------------------------------------------------- mean / GCN layer with the A operand handed over as tile images
+@pytest.mark.parametrize("kind", ["mean_concat", "mean_add", "gcn"])
+@pytest.mark.parametrize("shape", [(5632, 602, 128, True), (301, 50, 16, False), (1000, 256, 40, True), (129, 33, 8, False)])
+def test_image_layer_bit_identical_to_fp32_pair(gs, kind, shape):
+    """gs_gather_mean_img + gs_sage_gemm_img (A operand as tf32 hi/lo tile images written by the gather) must reproduce
+    gs_gather_mean + gs_sage_gemm(tf32x3) bit for bit: same split, same products, same order."""
+    rows, F, D, two_hops = shape
+    rs = np.random.RandomState(rows + F)
+    n_src = 4000
+    table = torch.zeros((n_src + 1, gs.ops.pad_cols(F)), dtype=torch.float32, device="cuda")
+    table[:n_src, :F] = dev(rs.randn(n_src, F).astype(np.float32))
+    if two_hops:
+        n0 = rows // 11
+        n1 = rows - n0
+        s0 = dev(rs.randint(0, n_src + 1, size=n0).astype(np.int32))
+        s1 = dev(rs.randint(0, n_src + 1, size=n1).astype(np.int32))
+        s2 = dev(rs.randint(0, n_src + 1, size=n1 * 25).astype(np.int32))
+        s1n = dev(rs.randint(0, n_src + 1, size=n0 * 10).astype(np.int32))
+        segs = [gs.ops.Seg(n0, 10, self_ids=s0, neigh_ids=s1n, out_row0=0), gs.ops.Seg(n1, 25, self_ids=s1, neigh_ids=s2, out_row0=n0)]
+    else:
+        segs = [gs.ops.Seg(rows, 7, self_ids=dev(rs.randint(0, n_src, size=rows).astype(np.int32)),
+                           neigh_ids=dev(rs.randint(0, n_src, size=rows * 7).astype(np.int32)))]
+    gs.set_default_math("tf32x3")
+    old_small = gs.ops.SMALL_LAYER_MAX_ROWS
+    gs.ops.SMALL_LAYER_MAX_ROWS = 0
+    try:
+        if kind == "gcn":
+            agg = gs.GCNAggregator(F, 2 * D, bias=True)
+        else:
+            agg = gs.MeanAggregator(F, D, concat=(kind == "mean_concat"), bias=True)
+        agg.vars["bias"] = dev(rs.randn(agg.vars["bias"].numel()).astype(np.float32))
+        outs = {}
+        for use in (True, False):
+            gs.aggregators.USE_GEMM_IMAGES[0] = use
+            launches0 = gs.ops.LAUNCHES
+            outs[use] = agg.aggregate_rows(table[:, :F], segs).clone()
+            torch.cuda.synchronize()
+        assert torch.equal(outs[True], outs[False]), float((outs[True] - outs[False]).abs().max())
+        # and against the oracle
+        t = table[:, :F].cpu().numpy()
+        ref_rows = []
+        for sg in segs:
+            selfv = t[sg.self_ids.cpu().numpy()[:sg.n]]
+            neigh = t[sg.neigh_ids.cpu().numpy()[:sg.n * sg.k]].reshape(sg.n, sg.k, F)
+            if kind == "gcn":
+                ref_rows.append(oracle.gcn_aggregator(selfv, neigh, agg.vars["weights"].cpu().numpy(), act=lambda x: x))
+            else:
+                ref_rows.append(oracle.mean_aggregator(selfv, neigh, agg.vars["neigh_weights"].cpu().numpy(),
+                                                       agg.vars["self_weights"].cpu().numpy(), concat=(kind == "mean_concat"),
+                                                       act=lambda x: x))
+        ref = np.maximum(np.vstack(ref_rows) + agg.vars["bias"].cpu().numpy(), 0)
+        assert rel_err(outs[True].cpu().numpy(), ref) < TOL
+    finally:
+        gs.aggregators.USE_GEMM_IMAGES[0] = False
+        gs.ops.SMALL_LAYER_MAX_ROWS = old_small
+        gs.set_default_math("fp32")

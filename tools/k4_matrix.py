@@ -29,10 +29,12 @@ def timeit(n=16):
 
 
 flops = 2.0 * B * 250 * F * H
-for name, ksel, prod, tile, pipes, cluster in (("tmem 128 + cluster multicast", 0, 1, 128, 1, 1), ("tmem 128-row tiles", 0, 1, 128, 1, 0),
+for name, ksel, prod, tile, pipes, cluster in (("tmem 128 + cluster of 4", 0, 1, 128, 1, 4), ("tmem 128 + cluster of 2", 0, 1, 128, 1, 2), ("tmem 128-row tiles", 0, 1, 128, 1, 0),
                                                ("tmem 128 x 2 pipelines", 0, 1, 128, 2, 0), ("tmem 256-row tiles", 0, 1, 256, 1, 0),
                                                ("wide128 + TMA gather4", 3, 1, 128, 1, 0), ("wide128 + cp.async", 3, 0, 128, 1, 0),
                                                ("wide256 + cp.async", 2, 0, 256, 1, 0), ("round 1", 1, 0, 128, 1, 0)):
+    if os.environ.get("K4_MATRIX_ONLY") and not name.startswith(os.environ["K4_MATRIX_ONLY"]):
+        continue
     lib.gs_set_tuning(b"k4_kernel", ksel)
     lib.gs_set_tuning(b"k4_wide_producer", prod)
     lib.gs_set_tuning(b"k4_tile", tile)
@@ -44,4 +46,4 @@ lib.gs_set_tuning(b"k4_kernel", 0)
 lib.gs_set_tuning(b"k4_wide_producer", 1)
 lib.gs_set_tuning(b"k4_tile", 128)
 lib.gs_set_tuning(b"k4_pipes", 1)
-lib.gs_set_tuning(b"k4_cluster", 1)
+lib.gs_set_tuning(b"k4_cluster", 2)
