@@ -177,7 +177,7 @@ def main():
     ap.add_argument("--repeats", type=int, default=0,
                     help="how many times each K-step timed region is repeated (median reported); 0 = auto (~0.3 s per leg)")
     ap.add_argument("--no-config3", action="store_true", help="skip the short max-pool/bf16 pass behind roofline_tensor")
-    ap.add_argument("--workload", default="reddit", choices=["reddit", "unsup", "rmat"],
+    ap.add_argument("--workload", default="reddit", choices=["reddit", "unsup", "rmat", "train"],
                     help="reddit = BASELINE configs[1] (default; the contract line); unsup = configs[3]: unsupervised training "
                          "step, node-partitioned, data parallel; rmat = configs[4]: R-MAT graph, CSR sampler, partitioned")
     ap.add_argument("--rmat-scale", type=int, default=20, help="log2 of the R-MAT id space (27 = BASELINE configs[4])")
@@ -232,6 +232,9 @@ def main():
     if args.workload == "unsup":
         import bench_extra
         return bench_extra.run_unsup(args, g, rank, world, local_rank, dist, dev)
+    if args.workload == "train":
+        import bench_extra
+        return bench_extra.run_train(args, g, rank, world, local_rank, dist, dev)
     tdtype = torch.bfloat16 if kind == "maxpool" else torch.float32
     table = torch.zeros((N_NODES + 1, ops.pad_cols(F)), dtype=tdtype, device=dev)
     table[:, :F] = torch.from_numpy(g["features"]).to(dev).to(tdtype)

@@ -98,6 +98,51 @@ def run_unsup(args, g, rank, world, local_rank, dist, dev):
                 "= autograd with library GEMMs, eager launches (no CUDA graph): the step is launch-bound, not HBM-bound"}))
 
 
+def run_train(args, g, rank, world, local_rank, dist, dev):
+    """the SUPERVISED training step (reference graphsage/supervised_models.py:91-126): forward through the
+    kernels, cross-entropy over 41 classes, backward (autograd formulas with library GEMMs), gradients clipped to +-5, Adam.
+    One step = one 512-seed batch; the table is replicated (world == 1) - this is the training-throughput number that sits
+    beside the CPU port's forward+backward."""
+    import graphsage_b200 as gs
+    gs.set_default_math(args.math)
+    n_classes = 41
+    table = torch.zeros((N_NODES + 1, gs.ops.pad_cols(F)), dtype=torch.float32, device=dev)
+    table[:, :F] = torch.from_numpy(g["features"]).to(dev)
+    adj_dev = torch.from_numpy(g["adj"]).to(dev)
+    sampler = gs.UniformNeighborSampler(adj_dev, seed=123)
+    infos = [gs.SAGEInfo("node", sampler, FANOUT[0], DIM), gs.SAGEInfo("node", sampler, FANOUT[1], DIM)]
+    model = gs.SupervisedGraphsage(n_classes, {"batch_size": BATCH, "dropout": 0.}, table[:, :F], adj_dev, None, infos, concat=True,
+                                   aggregator_type="mean", sigmoid_loss=False, learning_rate=0.01, device=dev,
+                                   distributed=world > 1)
+    rs = np.random.RandomState(4000 + rank)
+    total = args.warmup + args.steps
+    seeds = torch.from_numpy(rs.randint(0, N_NODES, size=(total, BATCH)).astype(np.int32)).to(dev)
+    labels = torch.nn.functional.one_hot(torch.from_numpy(g["comm"][seeds.cpu().numpy().reshape(-1)].astype(np.int64)),
+                                         n_classes).float().reshape(total, BATCH, n_classes).to(dev)   # label = community
+    for i in range(args.warmup):
+        model.train_step(seeds[i], labels[i])
+    _sync(dist, dev)
+    l0 = gs.ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    losses = []
+    for i in range(args.steps):
+        losses.append(model.train_step(seeds[args.warmup + i], labels[args.warmup + i]))
+    e1.record()
+    _sync(dist, dev)
+    ms = _max_over_ranks(dist, dev, e0.elapsed_time(e1))
+    launches = gs.ops.LAUNCHES - l0
+    if rank != 0:
+        return
+    print(json.dumps({
+        "metric": "training_seed_nodes_per_sec", "workload": "supervised graphsage_mean training step (fwd + bwd + clipped Adam), "
+        "reddit-shape synthetic, 2-hop 25x10, batch %d, 41 classes (label = community)" % BATCH,
+        "value": world * BATCH * args.steps / (ms * 1e-3), "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+        "loss_first": float(losses[0]), "loss_last": float(losses[-1]), "gpu_launches": launches,
+        "note": "forward = the library's kernels, backward = autograd formulas with library (cuBLAS) GEMMs; eager launches, no CUDA graph"}))
+
+
 def run_rmat(args, rank, world, local_rank, dist, dev):
     """configs[4]: R-MAT graph (a, b, c, d = 0.57, 0.19, 0.19, 0.05; --rmat-scale / --rmat-nodes; BASELINE: scale 27 trimmed to
     10^8 nodes, ~20 entries per node), F = 256, graphsage_mean 2-hop 25x10, batch 512.  The graph is generated ON the GPU

@@ -391,6 +391,130 @@ __global__ void __launch_bounds__(192) gather_mean_tma2_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------
+// gather + mean over a BFLOAT16 table (BASELINE.md's 160.9 MB bf16 gather yardstick): the structure of
+// gather_mean_tma2_kernel - whole rows (1,216 B at F = 602) fetched by cp.async.bulk in groups of kGroupRows through a
+// two-buffer ring - with the rows widened to fp32 as they are summed (fp32 accumulate, j order, like the fp32 kernel), so
+// the result equals the fp32 kernel's on the bf16-rounded table.  A thread owns 8 columns (one 128-bit shared load).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192) gather_mean_bf16_tma2_kernel(const uint16_t* __restrict__ src, int64_t n_src_rows, int F,
+                                                                    int64_t pitch, const __grid_constant__ SegTable tab,
+                                                                    int include_self, float* __restrict__ out_self,
+                                                                    float* __restrict__ out_mean, int64_t out_pitch,
+                                                                    int row_bytes) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar[2];
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int ncol8 = (int)(out_pitch >> 3);
+  const int row_u4 = row_bytes >> 4;
+  const size_t buf_bytes = (size_t)kGroupRows * row_bytes;
+  int64_t r_issue = blockIdx.x;
+  int g_issue = 0;
+  auto issue = [&](int buf) -> bool {
+    if (r_issue >= tab.total_rows) return false;
+    int64_t i;
+    const gs_segment& sg = tab.s[find_segment(tab, r_issue, i)];
+    const int k = sg.k;
+    const int rows_total = k + 1;
+    const int first = g_issue * kGroupRows;
+    const int cnt = min(kGroupRows, rows_total - first);
+    if (threadIdx.x < 32) {
+      if (threadIdx.x == 0) mbar_expect_tx(&bar[buf], (uint32_t)(cnt * row_bytes));
+      __syncwarp();
+      for (int j = threadIdx.x; j < cnt; j += 32) {
+        const int jj = first + j;
+        int64_t id;
+        if (jj < k) id = sg.neigh_ids ? (int64_t)sg.neigh_ids[i * k + jj] : sg.neigh_row0 + i * k + jj;
+        else id = sg.self_ids ? (int64_t)sg.self_ids[i] : sg.self_row0 + i;
+        id = clamp_row(id, n_src_rows);
+        bulk_g2s(smem + buf * buf_bytes + (size_t)j * row_bytes, src + id * pitch, (uint32_t)row_bytes, &bar[buf]);
+      }
+    }
+    if (first + cnt >= rows_total) { r_issue += gridDim.x; g_issue = 0; } else { ++g_issue; }
+    return true;
+  };
+  auto widen = [](uint4 u, float (&v)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[2 * e] = __uint_as_float(w[e] << 16);
+      v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+    }
+  };
+  uint32_t phase[2] = {0u, 0u};
+  int buf = 0;
+  bool have = issue(0);
+  int64_t r = blockIdx.x;
+  int g = 0;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  const int c = threadIdx.x;                                // this thread's 8-column chunk (ncol8 <= blockDim)
+  while (have) {
+    const bool have_next = issue(buf ^ 1);
+    int64_t i;
+    const gs_segment& sg = tab.s[find_segment(tab, r, i)];
+    const int k = sg.k;
+    const int rows_total = k + 1;
+    const int first = g * kGroupRows;
+    const int cnt = min(kGroupRows, rows_total - first);
+    const bool last = first + cnt >= rows_total;
+    mbar_wait(&bar[buf], phase[buf]);
+    phase[buf] ^= 1u;
+    const uint4* rows = reinterpret_cast<const uint4*>(smem + buf * buf_bytes);
+    const int nn = last ? cnt - 1 : cnt;
+    if (c < ncol8 && c * 8 < F) {
+      for (int j = 0; j < nn; ++j) {
+        float v[8];
+        widen(rows[j * row_u4 + c], v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += v[e];
+      }
+    }
+    if (last) {
+      const int64_t orow = sg.out_row0 + i;
+      if (c < ncol8) {
+        float a[8], sv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { a[e] = 0.f; sv[e] = 0.f; }
+        if (c * 8 < F) {
+          widen(rows[(cnt - 1) * row_u4 + c], sv);
+          const float div = (float)(k + (include_self ? 1 : 0));
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float t = acc[e];
+            if (include_self) t += sv[e];
+            a[e] = (c * 8 + e < F) ? t / div : 0.f;
+            if (c * 8 + e >= F) sv[e] = 0.f;
+          }
+        }
+        float4* om = reinterpret_cast<float4*>(out_mean + orow * out_pitch) + 2 * c;
+        om[0] = make_float4(a[0], a[1], a[2], a[3]);
+        om[1] = make_float4(a[4], a[5], a[6], a[7]);
+        if (out_self) {
+          float4* os = reinterpret_cast<float4*>(out_self + orow * out_pitch) + 2 * c;
+          os[0] = make_float4(sv[0], sv[1], sv[2], sv[3]);
+          os[1] = make_float4(sv[4], sv[5], sv[6], sv[7]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+      }
+      r += gridDim.x;
+      g = 0;
+    } else {
+      ++g;
+    }
+    __syncthreads();
+    buf ^= 1;
+    have = have_next;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // plain row gather.  TMA variant: each lane of a one-warp CTA moves one row
 // global -> shared -> global entirely with the bulk-copy engine (no register traffic).
 // ------------------------------------------------------------------------------------------
@@ -794,7 +918,7 @@ int32_t gs_gather_rows(const void* feats, int32_t dtype, int64_t n_rows, int32_t
 int32_t gs_gather_mean(const void* src, int32_t dtype, int64_t n_src_rows, int32_t F, int64_t pitch,
                        const gs_segment* segments_host, int32_t n_segments, int32_t include_self, void* out_self,
                        void* out_mean, int64_t out_pitch, void* stream) {
-  GS_REQUIRE(dtype == GS_F32, "gs_gather_mean: only GS_F32 is implemented (dtype=%d)", dtype);
+  GS_REQUIRE(dtype == GS_F32 || dtype == GS_BF16, "gs_gather_mean: dtype %d (GS_F32 or GS_BF16)", dtype);
   GS_REQUIRE(n_segments >= 0 && n_segments <= GS_MAX_SEGMENTS, "gs_gather_mean: n_segments=%d (max %d)", n_segments,
              GS_MAX_SEGMENTS);
   GS_REQUIRE(segments_host || n_segments == 0, "gs_gather_mean: segments_host is NULL");
@@ -813,6 +937,34 @@ int32_t gs_gather_mean(const void* src, int32_t dtype, int64_t n_src_rows, int32
   GS_REQUIRE(src && out_mean, "gs_gather_mean: NULL pointer");
   GS_REQUIRE(F > 0 && pitch >= F && out_pitch >= F && n_src_rows > 0, "gs_gather_mean: bad F/pitch");
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == GS_BF16) {
+    // bf16 table -> fp32 means / self rows: the bulk-copy kernel only (rows must be 16-byte multiples)
+    const int64_t f8 = ((int64_t)F + 7) / 8 * 8;
+    if (!(gs::aligned16(src) && gs::aligned16(out_mean) && (!out_self || gs::aligned16(out_self)) && pitch % 8 == 0 &&
+          out_pitch % 8 == 0 && f8 <= pitch && f8 <= out_pitch && f8 / 8 <= 192)) {
+      gs::set_error("gs_gather_mean(GS_BF16): needs 16-byte aligned rows (pitch %% 8 == 0), out_pitch %% 8 == 0 and F <= 1536");
+      return GS_ERR_UNSUPPORTED;
+    }
+    const int32_t rc_attr = gs::ensure_dyn_smem((const void*)gs::gather_mean_bf16_tma2_kernel, 200 * 1024);
+    if (rc_attr != GS_OK) return rc_attr;
+    const int row_bytes = (int)(f8 * 2);
+    const size_t smem2 = (size_t)2 * gs::kGroupRows * row_bytes;
+    const int ncol8 = (int)(out_pitch / 8);
+    int threads = ((ncol8 + 31) / 32) * 32;
+    if (threads < 32) threads = 32;
+    GS_REQUIRE(threads <= 192, "gs_gather_mean(GS_BF16): out_pitch too wide");
+    int per_sm = (int)((224 * 1024) / (smem2 + 1024));
+    if (per_sm < 1) per_sm = 1;
+    int lim = gs::tuning("gather_ctas_per_sm", 8);
+    if (per_sm > lim) per_sm = lim;
+    int64_t blocks = tab.total_rows;
+    int64_t cap = (int64_t)gs::sm_count() * per_sm;
+    if (blocks > cap) blocks = cap;
+    gs::gather_mean_bf16_tma2_kernel<<<(unsigned)blocks, threads, smem2, st>>>((const uint16_t*)src, n_src_rows, F, pitch, tab,
+                                                                              include_self, (float*)out_self, (float*)out_mean,
+                                                                              out_pitch, row_bytes);
+    return gs::launch_check("gather_mean_bf16_tma2_kernel");
+  }
   const float* fsrc = (const float*)src;
   const bool vec_ok = gs::aligned16(src) && gs::aligned16(out_mean) && (!out_self || gs::aligned16(out_self)) &&
                       pitch % 4 == 0 && out_pitch % 4 == 0 && ((F + 3) / 4) * 4 <= pitch;

@@ -230,8 +230,8 @@ def gather_mean(src, segments, include_self=False, want_self=True, out_pitch=Non
     if hasattr(src, "c_table"):
         return _gather_mean_sharded(src, segments, include_self, want_self, out_pitch, out_mean, out_self)
     require_cuda(src)
-    if src.dtype != torch.float32 or src.dim() != 2 or src.stride(1) != 1:
-        raise ValueError("src must be a row-major float32 2-D tensor")
+    if src.dtype not in (torch.float32, torch.bfloat16) or src.dim() != 2 or src.stride(1) != 1:
+        raise ValueError("src must be a row-major float32 (or bfloat16) 2-D tensor")
     F = src.shape[1]
     if out_pitch is None:
         out_pitch = pad_cols(F)
@@ -242,7 +242,7 @@ def gather_mean(src, segments, include_self=False, want_self=True, out_pitch=Non
         out_self = torch.empty((rows, out_pitch), dtype=torch.float32, device=src.device)
     arr = (Segment * max(len(segments), 1))(*[s.c_struct() for s in segments])
     ev = _probe("gather_mean/%d" % rows)
-    check(lib().gs_gather_mean(ptr(src), _lib.GS_F32, src.shape[0], F, src.stride(0), arr, len(segments),
+    check(lib().gs_gather_mean(ptr(src), _dtype_code(src), src.shape[0], F, src.stride(0), arr, len(segments),
                                int(bool(include_self)), ptr(out_self) if want_self else 0, ptr(out_mean), out_pitch,
                                stream_ptr()))
     _launched(1 if rows else 0, ev)

@@ -139,6 +139,8 @@ int32_t gs_gather_rows(const void* feats, int32_t dtype, int64_t n_rows, int32_t
  *   out_mean[r] = (sum_j neigh_j (+ self if include_self)) / (k (+1 if include_self))
  *   out_self[r] = self row (only if out_self != NULL)
  * src is [n_src_rows, F] with `pitch`; F columns are produced, columns F..out_pitch-1 are zeroed.
+ * dtype GS_F32, or GS_BF16: a bfloat16 table (rows 16-byte multiples: pitch % 8 == 0, out_pitch % 8 == 0) summed in fp32 -
+ * the outputs stay fp32 and equal the fp32 kernel's on the bf16-rounded table (half the gathered bytes).
  * --------------------------------------------------------------------------------------------- */
 #define GS_MAX_SEGMENTS 4
 typedef struct {

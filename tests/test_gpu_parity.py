@@ -892,3 +892,40 @@ def test_image_layer_bit_identical_to_fp32_pair(gs, kind, shape):
         gs.aggregators.USE_GEMM_IMAGES[0] = False
         gs.ops.SMALL_LAYER_MAX_ROWS = old_small
         gs.set_default_math("fp32")
+
+
+# ---------------------------------------------------------------- bf16 feature table through the fused gather + mean
+def test_gather_mean_bf16_table(gs):
+    """gs_gather_mean(GS_BF16): fp32 means / self rows from a bfloat16 table - must equal the fp32 kernel on the
+    bf16-rounded table bit for bit (same fp32 sums in the same order), for both mean forms, ragged widths and pad columns."""
+    rs = np.random.RandomState(31)
+    for F, k, n in ((602, 25, 700), (602, 10, 64), (50, 7, 333), (256, 1, 100), (8, 128, 9)):
+        n_src = 3000
+        P = gs.ops.pad_cols(F)
+        x = rs.randn(n_src, F).astype(np.float32)
+        tb = torch.full((n_src, P), 5.0, dtype=torch.bfloat16, device="cuda")          # pad columns hold junk
+        tb[:, :F] = dev(x).to(torch.bfloat16)
+        tf = torch.zeros((n_src, P), dtype=torch.float32, device="cuda")
+        tf[:, :F] = tb[:, :F].float()
+        seg = [gs.ops.Seg(n, k, self_ids=dev(rs.randint(-1, n_src + 2, size=n).astype(np.int32)),
+                          neigh_ids=dev(rs.randint(0, n_src, size=n * k).astype(np.int32)))]
+        for include_self in (False, True):
+            a = gs.ops.gather_mean(tb[:, :F], seg, include_self=include_self)
+            b = gs.ops.gather_mean(tf[:, :F], seg, include_self=include_self)
+            assert a[1].dtype == torch.float32 and torch.equal(a[1], b[1]) and torch.equal(a[0], b[0]), (F, k, include_self)
+    # and through the model: graphsage_mean over a bf16 table vs the oracle on the rounded features
+    g = load_golden("khop")
+    n = g["adj"].shape[0] - 1
+    feats = np.vstack([rs.randn(n, 602).astype(np.float32), np.zeros((1, 602), np.float32)])
+    table = torch.zeros((n + 1, gs.ops.pad_cols(602)), dtype=torch.bfloat16, device="cuda")
+    table[:, :602] = dev(feats).to(torch.bfloat16)
+    seeds = rs.randint(0, n, size=48).astype(np.int32)
+    gs.set_default_math("fp32")
+    sampler = gs.UniformNeighborSampler(dev(g["adj"]), seed=4)
+    infos = [gs.SAGEInfo("node", sampler, 6, 32), gs.SAGEInfo("node", sampler, 4, 32)]
+    m = gs.SampleAndAggregate({"batch_size": 48, "dropout": 0.}, table[:, :602], dev(g["adj"]), None, infos, concat=True,
+                              aggregator_type="mean")
+    out = m.forward(dev(seeds), normalize=True).cpu().numpy()
+    aggs = [dict(type="mean", **{k_: v.cpu().numpy() for k_, v in a.vars.items()}) for a in m.aggregators]
+    ref = oracle.forward_2hop(g["adj"], bf16_round(feats), seeds, [6, 4], aggs, True, 4, 0, normalize=True)
+    assert rel_err(out, ref) < TOL
