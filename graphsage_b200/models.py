@@ -230,6 +230,11 @@ class GraphedForward(object):
         for info in model.layer_infos:
             if all(info.neigh_sampler is not s for s in samplers):
                 samplers.append(info.neigh_sampler)
+        if len(samplers) != 1:
+            # every sampler object would need its own device-side call counter advanced by ITS calls per step; with one
+            # shared counter replay r would not draw what eager step r draws.  The reference shares one sampler
+            # (supervised_train.py:152-159), so refuse the other case instead of mis-counting silently.
+            raise NotImplementedError("GraphedForward needs all layer_infos to share one neigh_sampler object")
         self.samplers = samplers
         self.base_counters = [s.counter for s in samplers]
         self.n_calls = len(model.layer_infos)
@@ -270,6 +275,9 @@ class GraphedForward(object):
                 state["g"].capture_end()
                 self.graphs.append(state["g"])
             self._reset_python_counters()
+            for s in samplers:
+                s.counter_dev = None          # the counter's address is baked into the graph; eager calls made while this
+                                              # runner is alive keep the documented host-side sequence
         torch.cuda.current_stream(dev).wait_stream(self.stream)
         self.replays = 0
         # the warm-up forwards and the capture pass advanced the device counter through the fused bump; rewind
