@@ -22,3 +22,21 @@ def test_gather4_producer_tile_walk_matches_direct_indexing():
         for kblocks in (1, 2, 3, 5, 6, 7, 8, 13, 19, 20):
             for tiles in (1, 2, 5, 14):
                 assert pm.check_producer_walk(sa, kblocks, tiles)
+
+
+def test_round2_handoffs_are_live_and_alias_free():
+    assert pm.sweep_round2(seeds=1) == 4 * (4 + 6)
+
+
+def test_round2_producer_walks_match_direct_indexing():
+    # the cluster kernel's producers step by MPC_PW = 4 K-blocks, the two-group cp.async producers by 2
+    for step in (2, 4):
+        for kblocks in (1, 2, 3, 4, 5, 9, 10, 19):
+            for tiles in (1, 2, 7):
+                assert pm.check_producer_walk(step, kblocks, tiles)
+
+
+def test_cluster_ring_size_must_be_a_multiple_of_the_producer_warps():
+    # why gs_maxpool_mlp_fused rounds n_stages down to a multiple of MPC_PW before launching the cluster kernel
+    msg = pm.cluster_ring_must_be_a_multiple_of_the_producer_warps()
+    assert msg is not None and ("aliasing" in msg or "refilled" in msg or "expected" in msg or "different K-blocks" in msg)

@@ -53,7 +53,8 @@ class Cta(object):
 
 
 def simulate(kind, sa, total_it, n_prod, cl=1, seed=0, stage_bytes=8192, max_steps=2000000):
-    """kind: 'rowsplit' (default kernel: every producer warp fills its rows of EVERY stage, lagged publish not modelled:
+    """kind: 'groups' (round-2 cp.async producers: n_prod warps in two groups; group g fills the stages it = g, g + 2, ...
+    and each of its warps arrives once per stage), 'rowsplit' (default kernel: every producer warp fills its rows of EVERY stage, lagged publish not modelled:
     arrive per warp), 'g4' (warp w fills whole stages it = w, w + n_prod, ...; the kernels use n_prod == sa), 'g4mc' (as g4 in each of cl CTAs, each
     issuing 1/cl of every stage to all CTAs).  Returns the number of scheduler steps."""
     rnd = random.Random(seed)
@@ -61,6 +62,9 @@ def simulate(kind, sa, total_it, n_prod, cl=1, seed=0, stage_bytes=8192, max_ste
     if kind == "rowsplit":
         for c in ctas:
             c.full = [MBarrier(n_prod) for _ in range(sa)]
+    if kind == "groups":
+        for c in ctas:
+            c.full = [MBarrier(n_prod // 2) for _ in range(sa)]
     inflight = []                                           # delayed events: (fire_step, fn)
     step = [0]
 
@@ -70,12 +74,17 @@ def simulate(kind, sa, total_it, n_prod, cl=1, seed=0, stage_bytes=8192, max_ste
     # ---- agents as generators: yield a predicate to wait on, or None to just take a step
     def producer(ci, w):
         c = ctas[ci]
-        its = range(total_it) if kind == "rowsplit" else range(w, total_it, n_prod)
+        if kind == "rowsplit":
+            its = range(total_it)
+        elif kind == "groups":
+            its = range(w // (n_prod // 2), total_it, 2)         # the warp's group takes every other K-block
+        else:
+            its = range(w, total_it, n_prod)
         for it in its:
             s, n = it % sa, it // sa
             yield lambda: c.empty[s].ready((n & 1) ^ 1, n)
-            if kind == "rowsplit":
-                if w == 0:
+            if kind in ("rowsplit", "groups"):
+                if w % (n_prod // 2 if kind == "groups" else n_prod) == 0:
                     assert c.retired[s], "stage refilled before its MMAs retired"
                     c.content[s], c.retired[s] = it, False
                 later(lambda s=s: c.full[s].arrive())            # copies land, fence, arrive
@@ -157,6 +166,34 @@ def sweep(seeds=3):
     return n
 
 
+def sweep_round2(seeds=2):
+    """The round-2 kernels: two-group cp.async producers over 4 / 8 / 12 / 14 stages (maxpool_mlp_tmem_kernel, wide), and the
+    cluster kernel - 4 producer warps, warp w owns the slots w, w + 4, ... of a ring whose size is a multiple of 4, clusters
+    of 2 and 4 CTAs, multicast fills and multicast commits (maxpool_mlp_tmemc_kernel)."""
+    n = 0
+    for kblocks, tiles in ((10, 3), (4, 5), (1, 9), (19, 2)):
+        total = kblocks * tiles
+        for seed in range(seeds):
+            for sa in (4, 8, 12, 14):
+                simulate("groups", sa, total, 8, seed=seed)
+                n += 1
+            for sa in (4, 8, 12):
+                for cl in (2, 4):
+                    simulate("g4mc", sa, total, 4, cl=cl, seed=seed, stage_bytes=16384)
+                    n += 1
+    return n
+
+
+def cluster_ring_must_be_a_multiple_of_the_producer_warps():
+    """4 stage-filling warps over a 6-slot ring: a slot changes owner from fill to fill, a wait can pass on a stale phase."""
+    try:
+        for seed in range(30):
+            simulate("g4mc", 6, 10 * 4, 4, cl=2, seed=seed, stage_bytes=16384)
+    except AssertionError as e:
+        return str(e)
+    return None
+
+
 def shows_the_aliasing_bug():
     """The design this model rejected: 8 stage-filling warps over 7 slots - a warp can be two fills ahead of a slot."""
     try:
@@ -170,6 +207,8 @@ def shows_the_aliasing_bug():
 if __name__ == "__main__":
     print("hand-off protocol model: %d simulations, no deadlock / aliasing / early refill / misordered K-block" % sweep())
     print("8 warps over 7 slots ->", shows_the_aliasing_bug())
+    print("round-2 kernels: %d simulations clean" % sweep_round2())
+    print("4 warps over a 6-slot cluster ring ->", cluster_ring_must_be_a_multiple_of_the_producer_warps())
 
 
 def check_producer_walk(sa, kblocks, tiles):
