@@ -283,10 +283,20 @@ class MaxPoolingAggregator(_SageAggregator):
                                         n=s.n, out=xs[s.out_row0:s.out_row0 + s.n])
             return self._finish([(xs, self.input_dim, self.vars["self_weights"]),
                                  (hmax, self.hidden_dim, self.vars["neigh_weights"])], self._combine())
+        # materialised form (fp32 / tf32 arithmetic, fanout > 128, wide inputs, sharded tables): the MLP is a plain GEMM over
+        # the gathered neighbour rows (widened to fp32 when the table is bf16), then the pooling kernel
         xs = torch.empty((rows, ops.pad_cols(src.shape[1])), dtype=torch.float32, device=dev)[:, :src.shape[1]]
         hmax = torch.empty((rows, self.hidden_dim), dtype=torch.float32, device=dev)
+        widen = torch.is_tensor(src) and src.dtype != torch.float32
         for s in segments:
             n, k = s.n, s.k
+            if widen:
+                nrows = ops.gather_rows_f32(src, ids=None if s.neigh_ids is None else s.neigh_ids[:n * k],
+                                            row0=s.neigh_row0, n=n * k)
+                ops.gather_rows_f32(src, ids=None if s.self_ids is None else s.self_ids[:n], row0=s.self_row0, n=n,
+                                    out=xs[s.out_row0:s.out_row0 + n])
+                hmax[s.out_row0:s.out_row0 + n] = self._pool(nrows, n, k)
+                continue
             if s.neigh_ids is not None:
                 nrows = ops.gather_rows(src, s.neigh_ids[:n * k])
             else:

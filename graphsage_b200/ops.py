@@ -223,6 +223,16 @@ def make_segment(n, k, self_ids=None, neigh_ids=None, self_row0=0, neigh_row0=0,
     return Seg(n, k, self_ids, neigh_ids, self_row0, neigh_row0, out_row0)
 
 
+
+def _check_out(t, rows, out_pitch, name):
+    """A caller-provided output of gather_mean: the library writes rows x out_pitch floats at row stride out_pitch."""
+    if t is None:
+        return
+    require_cuda(t)
+    if t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1 or t.stride(0) != out_pitch or t.shape[0] < rows:
+        raise ValueError("%s must be a float32 [>= %d, .] CUDA matrix with row stride out_pitch = %d" % (name, rows, out_pitch))
+
+
 def gather_mean(src, segments, include_self=False, want_self=True, out_pitch=None, out_mean=None, out_self=None):
     """Fused embedding_lookup + reduce_mean over the fanout (models.py:299 + aggregators.py:48 / :106-107).
     segments: list of Seg; returns (out_self or None, out_mean), each [rows, out_pitch].
@@ -236,6 +246,8 @@ def gather_mean(src, segments, include_self=False, want_self=True, out_pitch=Non
     if out_pitch is None:
         out_pitch = pad_cols(F)
     rows = max([s.out_row0 + s.n for s in segments] + [0])
+    _check_out(out_mean, rows, out_pitch, "out_mean")
+    _check_out(out_self if want_self else None, rows, out_pitch, "out_self")
     if out_mean is None:
         out_mean = torch.empty((rows, out_pitch), dtype=torch.float32, device=src.device)
     if want_self and out_self is None:
@@ -323,6 +335,8 @@ def _gather_mean_sharded(src, segments, include_self, want_self, out_pitch, out_
     if out_pitch is None:
         out_pitch = pad_cols(F)
     rows = max([s.out_row0 + s.n for s in segments] + [0])
+    _check_out(out_mean, rows, out_pitch, "out_mean")
+    _check_out(out_self if want_self else None, rows, out_pitch, "out_self")
     if out_mean is None:
         out_mean = torch.empty((rows, out_pitch), dtype=torch.float32, device=src.device)
     if want_self and out_self is None:

@@ -1,17 +1,22 @@
 """Multi-GPU: node-partitioned feature table with the halo exchange fused into the gather.
 
-One process per GPU (torch.distributed for bootstrap / barriers only).  Rank r owns the feature rows
-of global nodes [r*R, (r+1)*R); every rank maps every shard through CUDA IPC (NVLink / NVSwitch peer
-memory), and the gather kernels (gs_gather_mean_sharded / gs_gather_rows_sharded) resolve each id to
-`base[id // R] + (id % R) * pitch` - remote rows are pulled by the consuming kernel itself, so no
-staging buffer and no collective sits on the data path.  The reference is single-device
-(supervised_train.py:59); this is new design.
+One process per GPU (torch.distributed for bootstrap, seed routing, barriers and the training step's one gradient
+all-reduce).  Rank r owns the feature rows of the global nodes [row_start[r], row_start[r+1]) - equal ranges
+(`uniform_bounds`) or cuts moved to community starts (`community_bounds`); every rank maps every shard through CUDA IPC
+(NVLink / NVSwitch peer memory), and the gather kernels (gs_gather_mean_sharded / gs_gather_rows_sharded /
+gs_gather_mean_img) resolve each id to `base[owner] + (id - row_start[owner]) * pitch`: remote rows are pulled by the
+consuming kernel's own bulk copies, so no collective sits on the data path.  A rank may also keep replicas of the
+remote rows its batches read most (`hot_remote_rows`, `hot_remote_rows_csr`) behind its own rows; ids are then resolved
+once per step to locators (ops.translate_ids) and replica hits are local reads.  GS_HALO_STAGING=1 switches to the
+claim / fetch / translate staging pass (every remote row of a step crosses NVLink once; measured slower at 2 GPUs, so
+opt-in).  The reference is single-device (supervised_train.py:59); this is new design.
 
-Seeds are routed to their owner (owner-computes), so hop-0 self rows are always local; how many of the
-hop-1/hop-2 rows are remote is decided by the partition (relabel nodes by community first:
-`locality_order`).
+Seeds are routed to their owner (`route_seeds`, owner-computes), so hop-0 self rows are always local; how many of the
+hop-1 / hop-2 rows are remote is decided by the partition (relabel nodes by community first: `locality_order`) and by
+the replica budget (`default_cache_rows`).  Data-parallel training: `broadcast_parameters` + `allreduce_gradients`.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -236,7 +241,6 @@ class ShardedFeatures(object):
                 raise ValueError("replica_ids must be sorted, unique, in range and not owned by this rank")
         self.replica_ids = rep_ids
         self.shape = (self.n_nodes + 1, F)
-        import os
         self.stage_halo = os.environ.get("GS_HALO_STAGING", "0") == "1"   # opt-in: fetch every remote row of a step once (ops._gather_mean_sharded); measured slower at 2 GPUs
         self.pitch = pad_cols(F)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)

@@ -84,3 +84,26 @@ def test_pool_loss_and_gradients_match_cpu_autograd(kind, concat):
         assert rel_err(a.mlp_layers[0].vars["bias"].grad.cpu().numpy().reshape(1, -1),
                        ra["mlp_bias"].grad.numpy().reshape(1, -1), floor=1e-8) < 2e-4
     m.train_step(torch.from_numpy(seeds), torch.from_numpy(labels))      # clipped Adam over all variables incl. the MLP's
+
+
+def test_maxpool_fp32_arithmetic_over_a_bf16_table():
+    """A bf16 feature table with fp32 arithmetic takes the materialised pooling path (rows widened to fp32 by
+    gs_gather_rows_f32): same answer as the fp32 table holding the bf16-rounded values (reference aggregators.py:168-195)."""
+    import graphsage_b200 as gs
+    from conftest import bf16_round
+    g = load_golden("khop")
+    rs = np.random.RandomState(8)
+    n, f, B = 300, 50, 48
+    adj = np.ascontiguousarray(g["adj"][:, :32])
+    feats = bf16_round(np.vstack([rs.randn(n, f).astype(np.float32), np.zeros((1, f), np.float32)]))
+    seeds = rs.randint(0, n, size=B).astype(np.int32)
+    outs = []
+    gs.set_default_math("fp32")
+    for table in (torch.from_numpy(feats).cuda(), torch.from_numpy(feats).cuda().to(torch.bfloat16)):
+        gs.inits.manual_seed(11)
+        sampler = gs.UniformNeighborSampler(torch.from_numpy(adj).cuda(), seed=5)
+        infos = [gs.SAGEInfo("node", sampler, 25, 64), gs.SAGEInfo("node", sampler, 10, 64)]
+        m = gs.SampleAndAggregate({"batch_size": B, "dropout": 0.}, table, torch.from_numpy(adj).cuda(), None, infos,
+                                  concat=True, aggregator_type="maxpool")
+        outs.append(m.forward(torch.from_numpy(seeds), normalize=True).cpu().numpy())
+    assert rel_err(outs[1], outs[0]) < 1e-6
