@@ -1140,17 +1140,19 @@ __global__ void __launch_bounds__(MPT_THREADS, 1) maxpool_mlp_tmem_kernel(const 
   }
 }
 
-// Cluster form (k4_cluster = 1, the default when hidden / 128 is 2, 4 or 8): the CTAs that hold the hidden slices of ONE
-// tile form a thread-block cluster of CL = hidden / 128 CTAs.  Each CTA gathers only 128 / CL of the tile's rows - with the
-// TMA row gather, `cp.async.bulk.tensor.2d.tile::gather4` (four table rows named by index, 128 bytes each, SWIZZLE_128B
-// applied by the tensor map, columns >= K zero-filled) - and MULTICASTS them into the same stage of every CTA of the
-// cluster, so a gathered row crosses the L2 -> SM fabric once per tile instead of once per slice: 163 MB per launch
-// instead of 650 MB (the fabric, saturated by 128-byte random pieces at 5.4 TB/s, was what held every one-CTA-per-slice
-// variant at 121 us).  Hand-off: a CTA's full barrier = its own expect_tx arrive + 16 KB of transactions from all CL
-// issuers; its empty barrier counts CL arrivals - every CTA's MMA warp commits with .multicast::cluster to all CL empty
-// barriers -, so a stage is refilled only when the whole cluster has consumed it.  Producer warp w owns the ring slots
-// w, w + MPC_PW, ... (n_stages is a multiple of MPC_PW: a slot is always filled by the same warp, so a wait is never more
-// than one phase ahead - tools/pipeline_model.py).  No cp.async groups, no proxy fence, no per-thread address arithmetic.
+// Cluster form (the default; k4_cluster = cluster size CL, 2 unless tuned): CL of the CTAs that hold the hidden slices of
+// ONE tile form a thread-block cluster.  Each CTA gathers only 128 / CL of the tile's rows - with the TMA row gather,
+// `cp.async.bulk.tensor.2d.tile::gather4` (four table rows named by index, 128 bytes each, SWIZZLE_128B applied by the
+// tensor map, columns >= K zero-filled) - and MULTICASTS them into the same stage of every CTA of the cluster, so a
+// gathered row crosses the L2 -> SM fabric once per cluster instead of once per slice (650 MB per launch without
+// clusters, 325 MB with pairs, 163 MB with clusters of four).  Measured: the traffic cut alone did not move
+// the kernel - the MMA issue chain is what bounds it - but the producer side shrinks to one elected lane per warp with
+// no per-thread address arithmetic, no cp.async groups and no proxy fence, and pairs keep all 148 SMs busy (74 clusters)
+// where clusters of four fit only 33 (132 SMs): 111 us against 117 us at hop 2.  Hand-off: a CTA's full barrier = its own
+// expect_tx arrive + 16 KB of transactions from all CL issuers; its empty barrier counts CL arrivals - every CTA's MMA
+// warp commits with .multicast::cluster to all CL empty barriers -, so a stage is refilled only when the whole cluster
+// has consumed it.  Producer warp w owns the ring slots w, w + MPC_PW, ... (n_stages is a multiple of MPC_PW: a slot is
+// always filled by the same warp, so a wait is never more than one phase ahead - tools/pipeline_model.py).
 constexpr int MPC_PW = 4;                         // producer warps
 constexpr int MPC_THREADS = (MPC_PW + 6) * 32;
 
@@ -1964,7 +1966,7 @@ static int32_t pool_mlp_fused(const void* table_bf16, int64_t n_rows, int32_t K,
   prm.issue_elect = gs::tuning("mma_issue", 1) != 0;
   if (kernel_sel == 0) {
     const unsigned char* ws = (const unsigned char*)packed_weights;
-    const int nt = tile_rows;                         // 256 (default) or 128 (k4_tile = 128)
+    const int nt = tile_rows;                         // 128 (default) or 256 (k4_tile = 256)
     prm.kblocks = (K + 63) / 64;
     prm.G = nt / k;
     prm.n_tiles = (n_groups + prm.G - 1) / prm.G;
