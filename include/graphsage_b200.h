@@ -57,8 +57,17 @@ const char* gs_last_error_string(void);
  *   gather_ctas_per_sm (8)  grid cap of the LDG / simple gather kernels
  *   gemm_async (0)          gs_sage_gemm tcgen05 producers: 1 = cp.async staging instead of register prefetch
  *   mma_issue (1)           tcgen05 issue form: 1 = whole warp + elect.sync (tensor-pipe floor), 0 = single thread
- *   k4_producer (0)         gs_maxpool/meanpool_mlp_fused gather-A producers: 0 = cp.async, 1 = TMA tile::gather4,
- *                           2 = gather4 multicast over clusters of the hidden slices (both compiled, not yet measured)
+ *   k4_kernel (0)           gs_maxpool/meanpool_mlp_fused kernel family: 0 = weights in tensor memory, gathered rows = B
+ *                           operand (default); 3 / 2 = weights resident in shared memory, 128- / 256-row tiles; 1 = the
+ *                           round-1 form (gathered rows = A operand; k4_producer 0 cp.async, 1 gather4, 2 gather4 multicast)
+ *   k4_cluster (2)          k4_kernel 0: thread-block cluster size (2, 4, 8; -1 = hidden / 128; 0 = no clusters) - the CTAs
+ *                           of a cluster share one gathered tile through TMA gather4 multicast
+ *   k4_tile (128)           k4_kernel 0: rows per tile (128; 256 = the wide tile, which runs without clusters)
+ *   k4_pipes (1)            k4_kernel 0 without clusters: 2 = two half-ring pipelines / two accumulators
+ *   k4_stages (0)           k4_kernel 0: cap on the operand ring depth (0 = as many as fit)
+ *   k4_wide_producer (1)    k4_kernel 3: 1 = TMA gather4 producers, 0 = cp.async producers
+ *   halo_fetch_ctas_per_sm (2)  grid of gs_halo_fetch
+ * Every K4 variant is parity-tested (tests/test_gpu_parity.py: K4_VARIANTS); DESIGN.md section 4a has the measurements.
  * The Python host also reads them from the environment: GS_TUNING="key=value,key=value". */
 int32_t gs_set_tuning(const char* key, int32_t value);
 
