@@ -1719,7 +1719,10 @@ __global__ void __launch_bounds__((MP_SA + 6) * 32, 1)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Variant 2 (GS_TUNING=k4_producer=2; compiled, not yet run on a GPU): as the gather4 variant, plus thread-block clusters.
+// Variant 2 (k4_kernel=1 with k4_producer=2; run on a B200 in round 2 through tools/tc_check.py: bit-identical to the
+// cp.async producers, 259 us at hop 2 against 164 us for the gather4 variant without clusters - the round-1 geometry keeps
+// the gathered rows as the A operand, so a cluster of all slices serialises on one tile): as the gather4 variant, plus
+// thread-block clusters.
 // The n_slices CTAs that work on the SAME M tile (one per 128-wide slice of the hidden dimension) form a cluster of
 // CL = n_slices (2 or 4) CTAs; each gathers only 128 / CL of the tile's rows and MULTICASTS them into the A stage of
 // every CTA of the cluster, so an A row crosses the L2 -> SM fabric once per cluster instead of once per slice
