@@ -103,6 +103,44 @@ def test_route_seeds_gloo_world2():
     _run(_cpu_worker, 2)
 
 
+def _cpu_worker_world4(rank, world, port, q):
+    """The same host logic at four ranks (the driver's scaling run also uses N = 4): uneven bounds with an EMPTY shard,
+    routing, and the packed gradient all-reduce."""
+    try:
+        from graphsage_b200 import parallel
+        _init(rank, world, port, "gloo")
+        n_nodes = 1003
+        assert parallel.uniform_bounds(n_nodes, world) == [0, 251, 502, 753, 1003]
+        bounds = [0, 400, 400, 900, n_nodes]                    # shard 1 owns nothing
+        rs = np.random.RandomState(10 + rank)
+        seeds = torch.from_numpy(rs.randint(0, n_nodes, size=200 + 31 * rank).astype(np.int32))
+        for b in (None, bounds):
+            mine = parallel.route_seeds(seeds, n_nodes, row_start=b)
+            lo, hi = (parallel.uniform_bounds(n_nodes, world) if b is None else b)[rank:rank + 2]
+            assert bool(((mine >= lo) & (mine < hi)).all())
+            got, sent = [None] * world, [None] * world
+            dist.all_gather_object(got, mine.tolist())
+            dist.all_gather_object(sent, seeds.tolist())
+            assert sorted(sum(got, [])) == sorted(sum(sent, []))
+            if b is not None:
+                assert len(got[1]) == 0
+        p = [torch.zeros(7, requires_grad=True)]
+        p[0].grad = torch.full((7,), float(rank))
+        assert parallel.allreduce_gradients(p) == 28
+        assert torch.equal(p[0].grad, torch.full((7,), 1.5))     # mean of 0, 1, 2, 3
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def test_route_seeds_gloo_world4():
+    _run(_cpu_worker_world4, 4)
+
+
 def test_locality_relabel_preserves_graph():
     from graphsage_b200 import parallel
     from graphsage_b200.synthetic import community_graph_csr
